@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/*: index fixtures + golden query/answer vectors.
+
+Runs ONLY in the build container, where /root/reference exists: every index is built by the
+unmodified reference builder and every expected answer is produced by the unmodified reference
+dictionary (oracle/_ref/libsshash_ref{31,63}.so, see oracle/Makefile).  The outputs are committed
+so that the GPU box (which has no /root/reference) can check both the C oracle and the CUDA path
+against the reference's own answers.
+
+    python tests/golden/make_golden.py
+
+Fixtures (name: source file, k, m, mode, #sequences taken from the head of the file):
+"""
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+
+DATA = "/root/reference/data/unitigs_stitched/"
+TMP = "/tmp/sshash_golden_tmp"
+
+# name, source, k, m, canonical, nseq (None = whole file), build lib (31/63)
+FIXTURES = [
+    ("se_k31_m13", "salmonella_enterica_k31_ust.fa.gz", 31, 13, False, None, 31),   # BASELINE cfg 1/2
+    ("sal100_k31_m7_reg", "salmonella_100_k31_ust.fa.gz", 31, 7, False, 3000, 31),  # heavy buckets, 2 skew partitions
+    ("sal100_k31_m7_canon", "salmonella_100_k31_ust.fa.gz", 31, 7, True, 3000, 31),  # canonical + heavy
+    ("sal100_k31_m11_canon", "salmonella_100_k31_ust.fa.gz", 31, 11, True, 5000, 31),  # canonical, singleton+midload
+    ("sal100_k31_m7_reg_b63", "salmonella_100_k31_ust.fa.gz", 31, 7, False, 3000, 63),  # k<=31 written by the 63 build
+    ("se_k63_m21", "se.ust.k63.fa.gz", 63, 21, False, 60, 63),                        # 128-bit k-mers
+    ("se_k63_m7_reg", "se.ust.k63.fa.gz", 63, 7, False, 30, 63),                      # 128-bit + heavy (16-byte MPHF keys)
+    ("se_k63_m8_canon", "se.ust.k63.fa.gz", 63, 8, True, 30, 63),                     # 128-bit canonical + heavy
+    ("se_k47_m8", "se.ust.k47.fa.gz", 47, 8, False, 30, 63),                          # 32 < k < 63
+]
+NQ = 12000  # positives per fixture (+ as many negatives)
+
+
+def subset(src, nseq, dst):
+    with gzip.open(src, "rt") as f, open(dst, "w") as g:
+        c = 0
+        for line in f:
+            g.write(line)
+            if not line.startswith(">"):
+                c += 1
+                if nseq is not None and c >= nseq:
+                    break
+
+
+def rc_packed(x_lo, x_hi, k):
+    """reverse complement of packed k-mers (A0 C1 T2 G3; complement = xor 2) on python ints."""
+    out = []
+    for lo, hi in zip(x_lo.tolist(), x_hi.tolist()):
+        x = lo | (hi << 64)
+        y = 0
+        for i in range(k):
+            y |= (((x >> (2 * i)) & 3) ^ 2) << (2 * (k - 1 - i))
+        out.append(y)
+    return out
+
+
+def make_queries(d, rng, words):
+    n = d.num_kmers
+    k = d.k
+    pid = rng.integers(0, n, NQ).astype(np.uint64)
+    pid[:4] = [0, 1, n - 1, n - 2]
+    pos = d.access(pid).reshape(NQ, words)
+    lo = pos[:, 0].copy()
+    hi = pos[:, 1].copy() if words == 2 else np.zeros(NQ, dtype=np.uint64)
+    # odd-indexed positives are reverse-complemented (tools/perf.hpp:41-51)
+    rcs = rc_packed(lo[1::2], hi[1::2], k)
+    lo[1::2] = [y & (2**64 - 1) for y in rcs]
+    hi[1::2] = [y >> 64 for y in rcs]
+    # negatives: 1/2 uniform random k-mers, 1/2 single-base mutations of positives (same minimizer,
+    # absent k-mer -> exercises the bucket scan / heavy-bucket out-of-range path)
+    nneg = NQ
+    mask = (1 << (2 * k)) - 1
+    rnd = [int(a) | (int(b) << 64) for a, b in zip(rng.integers(0, 2**63, nneg // 2), rng.integers(0, 2**63, nneg // 2))]
+    rnd = [r & mask for r in rnd]
+    mut = []
+    for j in range(nneg - nneg // 2):
+        x = int(lo[j]) | (int(hi[j]) << 64)
+        p = int(rng.integers(0, k))
+        x ^= int(rng.integers(1, 4)) << (2 * p)
+        mut.append(x)
+    neg = rnd + mut
+    nlo = np.array([x & (2**64 - 1) for x in neg], dtype=np.uint64)
+    nhi = np.array([x >> 64 for x in neg], dtype=np.uint64)
+    lo = np.concatenate([lo, nlo])
+    hi = np.concatenate([hi, nhi])
+    if words == 1:
+        return pid, lo
+    return pid, np.stack([lo, hi], axis=1).reshape(-1)
+
+
+def synth_reads(d, rng, nreads, read_len=150):
+    """BASELINE cfg 3 shape: half substrings of indexed strings (random strand), half iid ACGT,
+    a few reads with an N, a few too short."""
+    k = d.k
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    words = d.words
+    reads = []
+    for r in range(nreads):
+        if r % 2 == 0:
+            # walk consecutive k-mer ids from a random start: a substring of one indexed string
+            start = int(rng.integers(0, d.num_kmers))
+            ids = np.arange(start, min(d.num_kmers, start + read_len - k + 1), dtype=np.uint64)
+            km = d.access(ids).reshape(len(ids), words)
+            def tostr(row):
+                x = int(row[0]) | ((int(row[1]) << 64) if words == 2 else 0)
+                return "".join("ACTG"[(x >> (2 * i)) & 3] for i in range(k))
+            s = tostr(km[0])
+            prev = km[0]
+            for row in km[1:]:
+                t = tostr(row)
+                if t[:-1] != s[-(k - 1):]:
+                    break  # crossed into the next string
+                s += t[-1]
+            if rng.integers(0, 2):
+                s = "".join(comp[c] for c in reversed(s))
+            if rng.integers(0, 4) == 0 and len(s) > 40:  # mutate one base in the middle
+                p = int(rng.integers(10, len(s) - 10))
+                s = s[:p] + comp[s[p]] + s[p + 1:]
+        else:
+            s = "".join("ACGT"[i] for i in rng.integers(0, 4, read_len))
+        if r % 97 == 5:
+            p = int(rng.integers(0, len(s)))
+            s = s[:p] + "N" + s[p + 1:]
+        if r % 131 == 7:
+            s = s[: int(rng.integers(1, k))]
+        if r % 53 == 3:
+            s = s.lower()
+        reads.append(s)
+    return reads
+
+
+def main():
+    os.makedirs(TMP, exist_ok=True)
+    manifest = {}
+    for name, src, k, m, canon, nseq, lib in FIXTURES:
+        fa = os.path.join(TMP, name + ".fa")
+        subset(DATA + src, nseq, fa)
+        idx = os.path.join(HERE, name + ".sshash")
+        ref.build(fa, k, m, idx, canonical=canon, tmp_dir=TMP, max_k=lib)
+        d = ref.RefDictionary(idx, max_k=lib)
+        rng = np.random.default_rng(abs(hash(name)) % (2**32) if False else sum(map(ord, name)))
+        pid, q = make_queries(d, rng, d.words)
+        ids, full = d.lookup(q, check_rc=True, full=True)
+        ids_norc = d.lookup(q, check_rc=False)
+        assert (ids[:NQ] == pid).all(), name
+        reads = synth_reads(d, rng, 300 if k > 31 else 600)
+        bases = "".join(reads).encode()
+        offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+        sids, sfull, rep, _ = d.streaming_reads(bases, offs, full=True)
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            queries=q, positive_ids=pid, ids=ids, ids_norc=ids_norc, full=full,
+            read_bases=np.frombuffer(bases, dtype=np.uint8), read_offsets=offs,
+            stream_ids=sids, stream_full=sfull,
+            stream_report=np.array([rep[n] for n in ("num_kmers", "num_positive_kmers", "num_negative_kmers",
+                                                     "num_invalid_kmers", "num_searches", "num_extensions")],
+                                   dtype=np.uint64),
+        )
+        manifest[name] = dict(source=src, k=k, m=m, canonical=canon, nseq=nseq, max_k=lib,
+                              num_kmers=d.num_kmers, num_strings=d.num_strings,
+                              index_bytes=os.path.getsize(idx), stream_report=rep,
+                              num_found=int((ids != 2**64 - 1).sum()))
+        print(name, manifest[name])
+        d.close()
+    with open(os.path.join(HERE, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
