@@ -1,0 +1,606 @@
+// api.cu -- the C ABI declared in include/sshash_gpu.h: index upload, host<->device pipelines.
+//
+// There is no CPU fallback anywhere in this file: every compute entry point launches the sm_100a
+// kernels of kernels.cu or fails with SSHASH_GPU_ECUDA.
+#include <cuda_runtime.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sshash_gpu.h"
+#include "index_file.hpp"
+#include "kernels.cuh"
+
+using namespace sshash_b200;
+
+#define SSHASH_STR2(x) #x
+#define SSHASH_STR(x) SSHASH_STR2(x)
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(SSHASH_GPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+constexpr uint64_t kPadBytes = 64;   // zero tail after every array (>= 2 words for funnel reads)
+
+// One in-flight chunk of a host<->device pipeline.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void* d_in = nullptr; uint64_t in_cap = 0;
+    void* d_out = nullptr; uint64_t out_cap = 0;
+};
+
+// Device scratch owned by one call at a time (taken from / returned to the dictionary's pool).
+struct Workspace {
+    static constexpr int kSlots = 3;
+    Slot slots[kSlots];
+    // streaming scratch
+    void* d_bases = nullptr; uint64_t bases_cap = 0;
+    uint64_t* d_read_offsets = nullptr; uint64_t ro_cap = 0;
+    uint64_t* d_win_offsets = nullptr; uint64_t wo_cap = 0;
+    uint64_t* d_block_sums = nullptr; uint64_t bs_cap = 0;
+    uint64_t* d_win_id = nullptr; uint64_t* d_win_aux = nullptr; uint64_t win_cap = 0;
+    uint64_t* d_ids = nullptr; uint64_t ids_cap = 0;
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* h_counters = nullptr;   // pinned
+
+    ~Workspace() {
+        for (auto& s : slots) {
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        cudaFree(d_bases); cudaFree(d_read_offsets); cudaFree(d_win_offsets); cudaFree(d_block_sums);
+        cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters);
+        if (h_counters) cudaFreeHost(h_counters);
+    }
+};
+
+template <typename T>
+cudaError_t ensure(T*& p, uint64_t& cap, uint64_t need_bytes) {
+    if (need_bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    uint64_t bytes = need_bytes + need_bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+}
+
+bool is_device_pointer(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct sshash_gpu_dict {
+    int device = 0;
+    int sm_count = 148;
+    DeviceIndex ix{};
+    sshash_gpu_info_t info{};
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<std::unique_ptr<Workspace>> pool;
+
+    std::unique_ptr<Workspace> take() {
+        std::lock_guard<std::mutex> g(mu);
+        if (pool.empty()) return std::make_unique<Workspace>();
+        auto w = std::move(pool.back());
+        pool.pop_back();
+        return w;
+    }
+    void give(std::unique_ptr<Workspace> w) {
+        std::lock_guard<std::mutex> g(mu);
+        pool.push_back(std::move(w));
+    }
+    ~sshash_gpu_dict() {
+        cudaSetDevice(device);
+        pool.clear();
+        for (void* p : allocs) cudaFree(p);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+struct WorkspaceLease {
+    sshash_gpu_dict* d;
+    std::unique_ptr<Workspace> w;
+    explicit WorkspaceLease(const sshash_gpu_dict* dict) : d(const_cast<sshash_gpu_dict*>(dict)), w(d->take()) {}
+    ~WorkspaceLease() { d->give(std::move(w)); }
+    Workspace* operator->() { return w.get(); }
+};
+
+// ---- index upload ------------------------------------------------------------------------------
+struct Uploader {
+    sshash_gpu_dict* d;
+    uint64_t bytes = 0;
+    std::string error;
+
+    void* raw(const void* src, uint64_t n_bytes) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, n_bytes + kPadBytes);
+        if (e != cudaSuccess) { error = std::string("cudaMalloc: ") + cudaGetErrorString(e); return nullptr; }
+        d->allocs.push_back(p);
+        bytes += n_bytes + kPadBytes;
+        e = cudaMemset(static_cast<uint8_t*>(p) + n_bytes, 0, kPadBytes);
+        if (e == cudaSuccess && n_bytes) e = cudaMemcpy(p, src, n_bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { error = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return nullptr; }
+        return p;
+    }
+    DevCompact compact(const IndexFile& f, const CompactVectorView& c) {
+        DevCompact o{};
+        o.data = static_cast<const uint64_t*>(raw(f.ptr(c.data), c.data.bytes()));
+        o.size = c.size; o.mask = c.mask; o.width = (uint32_t)c.width;
+        return o;
+    }
+};
+
+uint64_t shift_mix(uint64_t v) { return v ^ (v >> 47); }
+
+int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
+    Uploader up{d};
+    DeviceIndex& ix = d->ix;
+    ix.k = f.k; ix.m = f.m; ix.canonical = f.canonical ? 1 : 0;
+    ix.kmer_words = max_k == 31 ? 1 : 2;
+    ix.magic = f.hasher_magic;
+    ix.num_kmers = f.num_kmers; ix.num_strings = f.num_strings;
+    ix.strings = static_cast<const uint64_t*>(up.raw(f.ptr(f.strings.data), f.strings.data.bytes()));
+    ix.strings_bits = f.strings.num_bits;
+
+    // MPHFs: one pilots pool + one decoded free-slot pool + one table of partitions
+    std::vector<const PartitionedPhfView*> phfs;
+    phfs.push_back(&f.minimizers_mphf);
+    for (auto const& s : f.skew_mphfs) phfs.push_back(&s);
+    uint64_t pilot_words = 0, n_parts = 0;
+    for (auto* p : phfs) for (auto const& sp : p->parts) { pilot_words += sp.pilots.data.n; ++n_parts; }
+    std::vector<DevPhfPart> parts; parts.reserve(n_parts);
+    std::vector<uint32_t> free_pool;
+    uint64_t* d_pilots = nullptr;
+    {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_pilots), pilot_words * 8 + kPadBytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pilots)");
+        d->allocs.push_back(d_pilots);
+        up.bytes += pilot_words * 8 + kPadBytes;
+        CU(cudaMemset(reinterpret_cast<uint8_t*>(d_pilots) + pilot_words * 8, 0, kPadBytes));
+    }
+    uint64_t word = 0;
+    std::vector<uint64_t> first_part;
+    for (auto* p : phfs) {
+        first_part.push_back(parts.size());
+        for (size_t i = 0; i != p->parts.size(); ++i) {
+            auto const& sp = p->parts[i];
+            if (sp.num_keys >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: MPHF partition with >= 2^32 keys");
+            DevPhfPart o{};
+            o.offset = p->offsets[i];
+            o.num_keys = sp.num_keys; o.table_size = sp.table_size; o.num_buckets = sp.num_buckets;
+            o.pilots_word = word; o.pilot_mask = sp.pilots.mask; o.pilot_width = (uint32_t)sp.pilots.width;
+            o.free_off = free_pool.size();
+            if (sp.pilots.data.n)
+                CU(cudaMemcpy(d_pilots + word, f.ptr(sp.pilots.data), sp.pilots.data.bytes(), cudaMemcpyHostToDevice));
+            word += sp.pilots.data.n;
+            const uint64_t n_free = sp.table_size - sp.num_keys;
+            if (n_free) {
+                size_t before = free_pool.size();
+                f.decode_elias_fano(sp.free_slots, n_free, free_pool);
+                if (free_pool.size() - before != n_free)
+                    return fail(SSHASH_GPU_EFORMAT, "malformed index file (free slots)");
+            }
+            parts.push_back(o);
+        }
+    }
+    ix.pilots = d_pilots;
+    ix.free_slots = static_cast<const uint32_t*>(up.raw(free_pool.data(), free_pool.size() * 4));
+    const DevPhfPart* d_parts = static_cast<const DevPhfPart*>(up.raw(parts.data(), parts.size() * sizeof(DevPhfPart)));
+    auto make_phf = [&](const PartitionedPhfView& p, uint64_t first) {
+        DevPhf o{};
+        const uint64_t k1 = 0xb492b66fbe98f273ull;
+        o.seed_hi = ~p.seed;
+        o.city_a = shift_mix(p.seed * k1) * k1;     // cityhash.cpp:245
+        o.city_cb = (~p.seed) * k1;                 // cityhash.cpp:246
+        o.num_partitions = p.parts.size();
+        o.parts = d_parts + first;
+        return o;
+    };
+    ix.mphf = make_phf(f.minimizers_mphf, first_part[0]);
+    ix.n_skew = (uint32_t)f.skew_mphfs.size();
+    for (uint32_t i = 0; i != ix.n_skew; ++i) {
+        ix.skew[i] = make_phf(f.skew_mphfs[i], first_part[1 + i]);
+        ix.skew_pos[i] = up.compact(f, f.skew_positions[i]);
+    }
+    ix.codewords = up.compact(f, f.control_codewords);
+    ix.mid_load = up.compact(f, f.mid_load_buckets);
+    ix.heavy = up.compact(f, f.heavy_load_buckets);
+    std::memset(ix.begin_buckets_of_size, 0, sizeof(ix.begin_buckets_of_size));
+    std::memcpy(ix.begin_buckets_of_size, f.ptr(f.begin_buckets_of_size), f.begin_buckets_of_size.bytes());
+
+    // string end-points: decoded + a sampled directory
+    std::vector<uint64_t> ends;
+    f.decode_endpoints(ends);
+    if (ends.size() != f.num_strings + 1 || ends.empty() || ends[0] != 0)
+        return fail(SSHASH_GPU_EFORMAT, "malformed index file (string end-points)");
+    for (size_t i = 1; i < ends.size(); ++i)
+        if (ends[i] <= ends[i - 1]) return fail(SSHASH_GPU_EFORMAT, "malformed index file (end-points not increasing)");
+    if (ends.size() >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: >= 2^32 strings");
+    const uint64_t U = ends.back();
+    ix.dir_shift = 8;
+    std::vector<uint32_t> dir((U >> ix.dir_shift) + 2);
+    {   // dir[h] = index of the last end-point < (h << shift), 0 if none
+        uint64_t j = 0;
+        for (uint64_t h = 0; h != dir.size(); ++h) {
+            const uint64_t lim = h << ix.dir_shift;
+            while (j + 1 < ends.size() && ends[j + 1] < lim) ++j;
+            dir[h] = (uint32_t)j;
+        }
+    }
+    ix.n_ends = ends.size();
+    ends.push_back(~0ull); ends.push_back(~0ull);   // scan sentinels
+    ix.ends = static_cast<const uint64_t*>(up.raw(ends.data(), ends.size() * 8));
+    ix.ends_dir = static_cast<const uint32_t*>(up.raw(dir.data(), dir.size() * 4));
+    if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
+    d->info.device_bytes = up.bytes;
+    return SSHASH_GPU_OK;
+}
+
+int check_dict(const sshash_gpu_dict* d) {
+    if (!d) return fail(SSHASH_GPU_EINVAL, "null dictionary handle");
+    cudaError_t e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return SSHASH_GPU_OK;
+}
+
+cudaError_t ensure_slot(Slot& s, uint64_t in_bytes, uint64_t out_bytes) {
+    cudaError_t e;
+    if (!s.stream) { e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+    if (in_bytes) { e = ensure(s.d_in, s.in_cap, in_bytes); if (e != cudaSuccess) return e; }
+    if (out_bytes) { e = ensure(s.d_out, s.out_cap, out_bytes); if (e != cudaSuccess) return e; }
+    return cudaSuccess;
+}
+
+// Generic batched pipeline for the per-query kernels (lookup / membership / access).
+//   in: n elements of in_elem bytes, out: n elements of out_elem bytes (either side host or device).
+// All-device: one asynchronous launch on the caller's stream.  Otherwise the batch is cut into
+// chunks that cycle through three slots (stream + staging buffers) so that the H2D copy of chunk
+// c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
+template <typename Launch>
+int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void* out, uint64_t out_elem, uint64_t n,
+                void* user_stream, Launch launch) {
+    if (n == 0) return SSHASH_GPU_OK;
+    const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
+    if (in_dev && out_dev) {
+        cudaStream_t s = user_stream ? static_cast<cudaStream_t>(user_stream) : d->stream;
+        CU(launch(in, out, n, s));
+        return SSHASH_GPU_OK;
+    }
+    WorkspaceLease ws(d);
+    const uint64_t chunk = std::max<uint64_t>(1, (32ull << 20) / std::max(in_elem, out_elem));
+    int c = 0;
+    for (uint64_t off = 0; off < n; off += chunk, ++c) {
+        const uint64_t cn = std::min(chunk, n - off);
+        Slot& s = ws->slots[c % Workspace::kSlots];
+        CU(ensure_slot(s, in_dev ? 0 : chunk * in_elem, out_dev ? 0 : chunk * out_elem));
+        const void* din = static_cast<const uint8_t*>(in) + off * in_elem;
+        void* dout = static_cast<uint8_t*>(out) + off * out_elem;
+        if (!in_dev) { CU(cudaMemcpyAsync(s.d_in, din, cn * in_elem, cudaMemcpyHostToDevice, s.stream)); din = s.d_in; }
+        void* kout = out_dev ? dout : s.d_out;
+        CU(launch(din, kout, cn, s.stream));
+        if (!out_dev) CU(cudaMemcpyAsync(dout, s.d_out, cn * out_elem, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ws->slots) if (s.stream) CU(cudaStreamSynchronize(s.stream));
+    return SSHASH_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sshash_gpu_last_error(void) { return g_last_error.c_str(); }
+
+const char* sshash_gpu_build_info(void) {
+    return "sshash_b200 CUDA " SSHASH_STR(CUDART_VERSION) " sm_100a";
+}
+
+uint64_t sshash_gpu_launch_count(void) { return kernel_launch_count(); }
+
+int sshash_gpu_open(const char* index_path, int device, int max_k, sshash_gpu_dict** out) {
+    if (!index_path || !out) return fail(SSHASH_GPU_EINVAL, "null argument");
+    *out = nullptr;
+    if (max_k != 0 && max_k != 31 && max_k != 63) return fail(SSHASH_GPU_EINVAL, "max_k must be 0, 31 or 63");
+    IndexFile f;
+    int st = SSHASH_GPU_OK;
+    std::string msg = f.open(index_path, &st);
+    if (st != SSHASH_GPU_OK) return fail(st, msg);
+    if (max_k == 0) max_k = f.k <= 31 ? 31 : 63;
+    if (f.k > (uint32_t)max_k) return fail(SSHASH_GPU_EINVAL, "k = " + std::to_string(f.k) + " needs max_k = 63");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SSHASH_GPU_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(SSHASH_GPU_EINVAL, "invalid device ordinal");
+    CU(cudaSetDevice(device));
+    auto d = std::make_unique<sshash_gpu_dict>();
+    d->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    d->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    sshash_gpu_info_t& in = d->info;
+    in.num_kmers = f.num_kmers; in.num_strings = f.num_strings; in.k = f.k; in.m = f.m;
+    in.canonical = f.canonical; in.weighted = f.weighted; in.max_k = (uint64_t)max_k;
+    in.version = (uint64_t)f.version[0] << 16 | (uint64_t)f.version[1] << 8 | f.version[2];
+    in.num_minimizers = f.minimizers_mphf.num_keys;
+    in.mphf_partitions = f.minimizers_mphf.parts.size();
+    in.skew_partitions = f.skew_mphfs.size();
+    in.index_file_bytes = f.file_bytes;
+    in.device = device;
+    st = upload_index(d.get(), f, max_k);
+    if (st != SSHASH_GPU_OK) return st;
+    CU(cudaDeviceSynchronize());
+    *out = d.release();
+    return SSHASH_GPU_OK;
+}
+
+int sshash_gpu_close(sshash_gpu_dict* dict) {
+    delete dict;
+    return SSHASH_GPU_OK;
+}
+
+int sshash_gpu_info(const sshash_gpu_dict* dict, sshash_gpu_info_t* out) {
+    if (!dict || !out) return fail(SSHASH_GPU_EINVAL, "null argument");
+    *out = dict->info;
+    return SSHASH_GPU_OK;
+}
+
+static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool ascii, uint64_t n, int check_rc,
+                         uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!queries || (!kmer_ids && !full)) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const uint64_t in_elem = ascii ? dict->ix.k : 8ull * dict->ix.kmer_words;
+    const DeviceIndex& ix = dict->ix;
+    const int sms = dict->sm_count;
+    const bool rc = check_rc != 0;
+    if (kmer_ids && full) {
+        // both outputs: ids are a column of the full records; produce the records, then the ids
+        if (is_device_pointer(queries) != is_device_pointer(kmer_ids) || is_device_pointer(queries) != is_device_pointer(full))
+            return fail(SSHASH_GPU_EINVAL, "kmers, kmer_ids and full must all be host or all be device pointers");
+        if (is_device_pointer(queries)) {
+            cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dict->stream;
+            CU(launch_lookup(ix, sms, queries, ascii, n, rc, kmer_ids, full, nullptr, s));
+            return SSHASH_GPU_OK;
+        }
+        st = run_batched(dict, queries, in_elem, full, sizeof(sshash_lookup_result), n, stream,
+                         [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                             return launch_lookup(ix, sms, in, ascii, cn, rc, nullptr, static_cast<sshash_lookup_result*>(out), nullptr, s);
+                         });
+        if (st) return st;
+        for (uint64_t i = 0; i != n; ++i) kmer_ids[i] = full[i].kmer_id;
+        return SSHASH_GPU_OK;
+    }
+    if (full)
+        return run_batched(dict, queries, in_elem, full, sizeof(sshash_lookup_result), n, stream,
+                           [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                               return launch_lookup(ix, sms, in, ascii, cn, rc, nullptr, static_cast<sshash_lookup_result*>(out), nullptr, s);
+                           });
+    return run_batched(dict, queries, in_elem, kmer_ids, 8, n, stream,
+                       [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                           return launch_lookup(ix, sms, in, ascii, cn, rc, static_cast<uint64_t*>(out), nullptr, nullptr, s);
+                       });
+}
+
+int sshash_gpu_lookup_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                            uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+    return lookup_common(dict, kmers, false, n, check_reverse_complement, kmer_ids, full, stream);
+}
+
+int sshash_gpu_lookup_batch_ascii(const sshash_gpu_dict* dict, const char* kmers, uint64_t n, int check_reverse_complement,
+                                  uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+    return lookup_common(dict, kmers, true, n, check_reverse_complement, kmer_ids, full, stream);
+}
+
+int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                               uint8_t* member, void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!kmers || !member) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const DeviceIndex& ix = dict->ix;
+    const int sms = dict->sm_count;
+    const bool rc = check_reverse_complement != 0;
+    return run_batched(dict, kmers, 8ull * ix.kmer_words, member, 1, n, stream,
+                       [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                           return launch_lookup(ix, sms, in, false, cn, rc, nullptr, nullptr, static_cast<uint8_t*>(out), s);
+                       });
+}
+
+int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n, uint64_t* kmers_out,
+                            void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!kmer_ids || !kmers_out) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const DeviceIndex& ix = dict->ix;
+    const int sms = dict->sm_count;
+    return run_batched(dict, kmer_ids, 8, kmers_out, 8ull * ix.kmer_words, n, stream,
+                       [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                           return launch_access(ix, sms, static_cast<const uint64_t*>(in), cn, static_cast<uint64_t*>(out), s);
+                       });
+}
+
+// One device-resident batch of reads: offsets scan, window lookups, state-machine replay.
+static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const char* d_bases, const uint64_t* d_read_offsets,
+                            uint64_t num_reads, uint64_t max_windows, uint64_t* d_ids_out, cudaStream_t s) {
+    const DeviceIndex& ix = dict->ix;
+    CU(ensure(w.d_win_offsets, w.wo_cap, (num_reads + 2) * 8));
+    CU(ensure(w.d_block_sums, w.bs_cap, window_offsets_scratch_words(num_reads) * 8));
+    if (max_windows > w.win_cap / 8 || !w.d_win_id || !w.d_win_aux) {
+        cudaFree(w.d_win_id); cudaFree(w.d_win_aux);
+        w.d_win_id = w.d_win_aux = nullptr; w.win_cap = 0;
+        uint64_t bytes = (max_windows + max_windows / 8 + 32) * 8;
+        CU(cudaMalloc(reinterpret_cast<void**>(&w.d_win_id), bytes));
+        CU(cudaMalloc(reinterpret_cast<void**>(&w.d_win_aux), bytes));
+        w.win_cap = bytes;
+    }
+    CU(launch_window_offsets(ix.k, d_read_offsets, num_reads, w.d_win_offsets, w.d_block_sums, s));
+    CU(launch_streaming(ix, dict->sm_count, d_bases, d_read_offsets, w.d_win_offsets, num_reads, w.d_win_id, w.d_win_aux,
+                        d_ids_out, w.d_counters, s));
+    return SSHASH_GPU_OK;
+}
+
+int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, const uint64_t* read_offsets, uint64_t num_reads,
+                               uint64_t* kmer_ids, sshash_streaming_report* report, void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (!report) return fail(SSHASH_GPU_EINVAL, "null report");
+    std::memset(report, 0, sizeof(*report));
+    if (num_reads == 0) return SSHASH_GPU_OK;
+    if (!bases || !read_offsets) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const bool dev = is_device_pointer(bases);
+    if (dev != is_device_pointer(read_offsets) || (kmer_ids && dev != is_device_pointer(kmer_ids)))
+        return fail(SSHASH_GPU_EINVAL, "bases, read_offsets and kmer_ids must all be host or all be device pointers");
+    WorkspaceLease ws(dict);
+    Workspace& w = *ws.w;
+    const uint32_t k = dict->ix.k;
+    if (!w.d_counters) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&w.d_counters), 8 * sizeof(unsigned long long)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&w.h_counters), 8 * sizeof(unsigned long long)));
+    }
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dict->stream;
+    CU(cudaMemsetAsync(w.d_counters, 0, 8 * sizeof(unsigned long long), s));
+    if (dev) {
+        // total bases bound the number of windows; two 8-byte reads tell us how many
+        uint64_t first = 0, last = 0;
+        CU(cudaMemcpyAsync(&first, read_offsets, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&last, read_offsets + num_reads, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        st = streaming_device(dict, w, bases, read_offsets, num_reads, last - first + 1, kmer_ids, s);
+        if (st) return st;
+    } else {
+        // chunks of reads: <= 64 MB of bases each, staged through the workspace buffers
+        const uint64_t max_bases = 64ull << 20;
+        uint64_t r0 = 0, win_done = 0;
+        std::vector<uint64_t> rel;
+        while (r0 < num_reads) {
+            uint64_t r1 = r0 + 1;
+            while (r1 < num_reads && read_offsets[r1 + 1] - read_offsets[r0] <= max_bases) ++r1;
+            const uint64_t nb = read_offsets[r1] - read_offsets[r0], nr = r1 - r0;
+            rel.resize(nr + 1);
+            uint64_t nwin = 0;
+            for (uint64_t i = 0; i <= nr; ++i) rel[i] = read_offsets[r0 + i] - read_offsets[r0];
+            for (uint64_t i = 0; i < nr; ++i) { uint64_t len = rel[i + 1] - rel[i]; if (len >= k) nwin += len - k + 1; }
+            CU(ensure(w.d_bases, w.bases_cap, nb + kPadBytes));
+            CU(ensure(w.d_read_offsets, w.ro_cap, (nr + 1) * 8));
+            if (kmer_ids) CU(ensure(w.d_ids, w.ids_cap, (nwin + 1) * 8));
+            CU(cudaMemcpyAsync(w.d_bases, bases + read_offsets[r0], nb, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(w.d_read_offsets, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, s));
+            st = streaming_device(dict, w, static_cast<const char*>(w.d_bases), w.d_read_offsets, nr, nwin + 1,
+                                  kmer_ids ? w.d_ids : nullptr, s);
+            if (st) return st;
+            if (kmer_ids && nwin) CU(cudaMemcpyAsync(kmer_ids + win_done, w.d_ids, nwin * 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));   // `rel` and the staging buffers are reused by the next chunk
+            win_done += nwin;
+            r0 = r1;
+        }
+    }
+    CU(cudaMemcpyAsync(w.h_counters, w.d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    report->num_kmers = w.h_counters[0];
+    report->num_searches = w.h_counters[1];
+    report->num_extensions = w.h_counters[2];
+    report->num_negative_kmers = w.h_counters[3];
+    report->num_invalid_kmers = w.h_counters[4];
+    report->num_positive_kmers = report->num_searches + report->num_extensions;   // streaming_query.hpp:113
+    return SSHASH_GPU_OK;
+}
+
+// Host-side file driver: same record structure as the reference's drivers (src/query.cpp:53-108):
+// FASTA = header line + one sequence line per record, FASTQ = 4 lines per record; gz through zlib.
+int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char* filename, int multiline,
+                                         sshash_streaming_report* report) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (!filename || !report) return fail(SSHASH_GPU_EINVAL, "null argument");
+    std::memset(report, 0, sizeof(*report));
+    std::string fn(filename);
+    auto ends_with = [&](const char* suf) {
+        size_t n = std::strlen(suf);
+        return fn.size() >= n && fn.compare(fn.size() - n, n, suf) == 0;
+    };
+    bool fastq;
+    if (ends_with(".fa.gz") || ends_with(".fasta.gz") || ends_with(".fa") || ends_with(".fasta")) fastq = false;
+    else if (ends_with(".fq.gz") || ends_with(".fastq.gz") || ends_with(".fq") || ends_with(".fastq")) fastq = true;
+    else {   // query.cpp:169-171: only a message on stderr, empty report
+        std::fprintf(stderr, "unsupported query file format\n");
+        return SSHASH_GPU_OK;
+    }
+    if (multiline && !fastq) return fail(SSHASH_GPU_EINVAL, "multiline FASTA is not supported by the GPU streaming driver");
+    gzFile gz = gzopen(filename, "rb");   // transparently reads uncompressed files too
+    if (!gz) return fail(SSHASH_GPU_EIO, "error in opening the file '" + fn + "'");
+    gzbuffer(gz, 1 << 20);
+    std::string bases;
+    std::vector<uint64_t> offsets{0};
+    std::vector<char> line(1 << 16);
+    auto getline = [&](std::string* dst) -> bool {   // false at EOF with nothing read
+        bool any = false;
+        for (;;) {
+            if (!gzgets(gz, line.data(), (int)line.size())) return any;
+            any = true;
+            size_t len = std::strlen(line.data());
+            bool eol = len && line[len - 1] == '\n';
+            if (eol) --len;
+            if (dst) dst->append(line.data(), len);
+            if (eol) return true;
+        }
+    };
+    sshash_streaming_report total{};
+    auto flush = [&]() -> int {
+        if (offsets.size() <= 1) return SSHASH_GPU_OK;
+        sshash_streaming_report r{};
+        int rc = sshash_gpu_streaming_batch(dict, bases.data(), offsets.data(), offsets.size() - 1, nullptr, &r, nullptr);
+        if (rc) return rc;
+        total.num_kmers += r.num_kmers; total.num_positive_kmers += r.num_positive_kmers;
+        total.num_negative_kmers += r.num_negative_kmers; total.num_invalid_kmers += r.num_invalid_kmers;
+        total.num_searches += r.num_searches; total.num_extensions += r.num_extensions;
+        bases.clear(); offsets.assign(1, 0);
+        return SSHASH_GPU_OK;
+    };
+    for (;;) {
+        if (!getline(nullptr)) break;                 // header
+        if (!getline(&bases)) { /* header without sequence: empty read */ }
+        offsets.push_back(bases.size());
+        if (fastq) { getline(nullptr); getline(nullptr); }   // '+' and quality
+        if (bases.size() >= (256u << 20)) { st = flush(); if (st) { gzclose(gz); return st; } }
+    }
+    gzclose(gz);
+    st = flush();
+    if (st) return st;
+    *report = total;
+    return SSHASH_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// device_index.cuh -- the HBM-resident mirror of an SSHash index and the device-side lookup.
+//
+// Layout in HBM (one cudaMalloc per array, 256-byte aligned, each padded with >= 2 zero words so
+// the two-word funnel reads below never leave the allocation):
+//   strings        u64[]  2 bits/base, all input strings concatenated (+ the reference's sentinel)
+//                         -- verbatim copy of spectrum_preserving_string_set::strings
+//   pilots         u64[]  every PTHash partition's `compact` pilot vector, packed back to back
+//                         (word-aligned), minimizer MPHF first, then the <= 8 skew-index MPHFs
+//   free_slots     u32[]  every partition's Elias-Fano free-slot list DECODED to plain integers
+//                         (replaces elias_fano::access + darray select: one 4-byte load)
+//   phf_parts      DevPhfPart[] per-partition constants + offsets into the two pools above
+//   codewords      u64[]  control_codewords compact vector, verbatim
+//   mid_load       u64[]  mid_load_buckets compact vector, verbatim
+//   heavy          u64[]  heavy_load_buckets compact vector, verbatim
+//   skew_pos[i]    u64[]  positions[i] compact vectors, verbatim
+//   ends           u64[]  string end-points DECODED from the endpoints_sequence (n = strings+1)
+//   ends_dir       u32[]  ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none):
+//                         replaces hints_0 + the unary scan of high_bits with one 4-byte load + a
+//                         short linear scan of `ends`
+// Everything else (k, m, seeds, widths, begin_buckets_of_size[65]) travels in the kernel
+// parameter block (`DeviceIndex`, < 1 KB, constant-cached).
+//
+// Reference semantics (file:line under /root/reference) are cited per function.
+#pragma once
+
+#include <cstdint>
+
+namespace sshash_b200 {
+
+struct DevCompact {            // bits::compact_vector read side, compact_vector.hpp:253-260
+    const uint64_t* data;
+    uint64_t size;
+    uint64_t mask;
+    uint32_t width;
+    uint32_t pad_;
+};
+
+struct DevPhfPart {            // one pthash::single_phf (single_phf.hpp:116-142) + its offset
+    uint64_t offset;           // partitioned_phf::partition::offset, partitioned_phf.hpp:20-38
+    uint64_t num_keys;
+    uint64_t table_size;
+    uint64_t num_buckets;
+    uint64_t pilots_word;      // first word of this partition's pilots inside the pilots pool
+    uint64_t pilot_mask;
+    uint64_t free_off;         // first free slot of this partition inside the free-slot pool
+    uint32_t pilot_width;
+    uint32_t pad_;
+};
+
+struct DevPhf {                // pthash::partitioned_phf, partitioned_phf.hpp:139-149
+    uint64_t seed_hi;          // ~seed  (CityHash seed pair {seed, ~seed}, hash_util.hpp:12-16)
+    uint64_t city_a;           // ShiftMix(seed * k1) * k1      -- seed-only terms of CityMurmur
+    uint64_t city_cb;          // (~seed) * k1                     hoisted to the host
+    uint64_t num_partitions;
+    const DevPhfPart* parts;
+};
+
+struct DeviceIndex {
+    uint32_t k, m;
+    uint32_t canonical;
+    uint32_t kmer_words;       // 1 (max_k 31 build) or 2 (max_k 63 build)
+    uint64_t magic;            // mixer_64::m_magic
+    uint64_t num_kmers;
+    uint64_t num_strings;
+    const uint64_t* strings;
+    uint64_t strings_bits;
+    const uint64_t* pilots;
+    const uint32_t* free_slots;
+    DevPhf mphf;
+    DevCompact codewords;
+    DevCompact mid_load;
+    DevCompact heavy;
+    uint32_t n_skew;
+    uint32_t dir_shift;
+    DevPhf skew[8];
+    DevCompact skew_pos[8];
+    const uint64_t* ends;
+    uint64_t n_ends;
+    const uint32_t* ends_dir;
+    uint32_t begin_buckets_of_size[65];
+    uint32_t pad_;
+};
+
+#ifdef __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// k-mer word types.  W = number of 64-bit words (1: k <= 31, 2: k <= 63).
+// ------------------------------------------------------------------------------------------------
+template <int W> struct Kmer;
+template <> struct Kmer<1> { uint64_t lo; };
+template <> struct Kmer<2> { uint64_t lo, hi; };
+
+__device__ __forceinline__ bool kmer_eq(Kmer<1> a, Kmer<1> b) { return a.lo == b.lo; }
+__device__ __forceinline__ bool kmer_eq(Kmer<2> a, Kmer<2> b) { return a.lo == b.lo && a.hi == b.hi; }
+__device__ __forceinline__ bool kmer_lt(Kmer<1> a, Kmer<1> b) { return a.lo < b.lo; }
+__device__ __forceinline__ bool kmer_lt(Kmer<2> a, Kmer<2> b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+
+__device__ __forceinline__ uint64_t low_mask(uint32_t bits) {  // bits in [0,64]
+    return bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+}
+
+// dna_uint_kmer_t::crc64, include/kmer.hpp:141-157: complement (xor 0b10 per base), then reverse
+// the order of the 32 two-bit groups.  __brevll reverses single bits, so the two bits inside each
+// group are swapped back afterwards.
+__device__ __forceinline__ uint64_t rc64(uint64_t x) {
+    uint64_t r = __brevll(x ^ 0xaaaaaaaaaaaaaaaaull);
+    return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
+}
+// reverse_complement_inplace, include/kmer.hpp:159-165
+__device__ __forceinline__ Kmer<1> kmer_rc(Kmer<1> x, uint32_t k) { return {rc64(x.lo) >> (64 - 2 * k)}; }
+__device__ __forceinline__ Kmer<2> kmer_rc(Kmer<2> x, uint32_t k) {
+    uint64_t hi = rc64(x.lo), lo = rc64(x.hi);  // halves swap
+    uint32_t s = 128 - 2 * k;                   // in [2, 126]
+    Kmer<2> r;
+    if (s >= 64) { r.lo = hi >> (s - 64); r.hi = 0; }
+    else { r.lo = (lo >> s) | (hi << (64 - s)); r.hi = hi >> s; }
+    return r;
+}
+// the reverse complement of an m-mer held in 64 bits (spss.hpp:95-98 does it through the k-mer type)
+__device__ __forceinline__ uint64_t mmer_rc(uint64_t x, uint32_t m) { return rc64(x) >> (64 - 2 * m); }
+
+// 64 bits of `data` starting at bit `pos` (bit_vector::get_word64, bit_vector.hpp:186-193; the
+// device copy is zero-padded, which is what the reference's bounds test amounts to)
+__device__ __forceinline__ uint64_t read_word64(const uint64_t* __restrict__ data, uint64_t pos) {
+    uint64_t w = pos >> 6;
+    uint32_t s = (uint32_t)pos & 63u;
+    uint64_t a = __ldg(data + w);
+    if (s == 0) return a;
+    uint64_t b = __ldg(data + w + 1);
+    return (a >> s) | (b << (64 - s));
+}
+
+// util::read_kmer_at(strings, k, 2*offset), include/util.hpp:248-257
+__device__ __forceinline__ Kmer<1> read_kmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t k, Kmer<1>*) {
+    return {read_word64(ix.strings, 2 * base_offset) & low_mask(2 * k)};
+}
+__device__ __forceinline__ Kmer<2> read_kmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t k, Kmer<2>*) {
+    uint64_t pos = 2 * base_offset, w = pos >> 6;
+    uint32_t s = (uint32_t)pos & 63u;
+    uint64_t a = __ldg(ix.strings + w), b = __ldg(ix.strings + w + 1);
+    Kmer<2> r;
+    if (s == 0) { r.lo = a; r.hi = b; }
+    else {
+        uint64_t c = __ldg(ix.strings + w + 2);
+        r.lo = (a >> s) | (b << (64 - s));
+        r.hi = (b >> s) | (c << (64 - s));
+    }
+    if (2 * k <= 64) { r.lo &= low_mask(2 * k); r.hi = 0; }
+    else r.hi &= low_mask(2 * k - 64);
+    return r;
+}
+__device__ __forceinline__ uint64_t read_mmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t m) {
+    return read_word64(ix.strings, 2 * base_offset) & low_mask(2 * m);
+}
+
+// compact_vector::access, compact_vector.hpp:253-260 (two aligned word loads instead of one
+// unaligned 8-byte load)
+__device__ __forceinline__ uint64_t compact_get(const uint64_t* __restrict__ data, uint32_t width, uint64_t mask, uint64_t i) {
+    uint64_t pos = i * width, w = pos >> 6;
+    uint32_t s = (uint32_t)pos & 63u;
+    uint64_t v = __ldg(data + w) >> s;
+    if (s + width > 64) v |= __ldg(data + w + 1) << (64 - s);
+    return v & mask;
+}
+__device__ __forceinline__ uint64_t compact_get(const DevCompact& c, uint64_t i) {
+    return compact_get(c.data, c.width, c.mask, i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// minimizer: util::compute_minimizer, include/util.hpp:262-283 with mixer_64::hash,
+// include/hash_util.hpp:91.  Leftmost strict minimum.
+// ------------------------------------------------------------------------------------------------
+struct Minimizer { uint64_t value; uint32_t pos; };
+
+#define SSHASH_MIX_C 0x517cc1b727220a95ull
+
+__device__ __forceinline__ Minimizer compute_minimizer(Kmer<1> x, uint32_t k, uint32_t m, uint64_t magic) {
+    const uint64_t mm = low_mask(2 * m);
+    uint64_t min_hash = ~0ull, mini = ~0ull, v = x.lo;
+    uint32_t pos = 0;
+    const uint32_t n = k - m + 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t mmer = v & mm;
+        uint64_t h = (mmer * SSHASH_MIX_C) ^ magic;
+        if (h < min_hash) { min_hash = h; mini = mmer; pos = i; }
+        v >>= 2;
+    }
+    return {mini, pos};
+}
+__device__ __forceinline__ Minimizer compute_minimizer(Kmer<2> x, uint32_t k, uint32_t m, uint64_t magic) {
+    const uint64_t mm = low_mask(2 * m);
+    uint64_t min_hash = ~0ull, mini = ~0ull, lo = x.lo, hi = x.hi;
+    uint32_t pos = 0;
+    const uint32_t n = k - m + 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t mmer = lo & mm;
+        uint64_t h = (mmer * SSHASH_MIX_C) ^ magic;
+        if (h < min_hash) { min_hash = h; mini = mmer; pos = i; }
+        lo = (lo >> 2) | (hi << 62);
+        hi >>= 2;
+    }
+    return {mini, pos};
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTHash evaluation.  CityHash128WithSeed restricted to 8- and 16-byte keys:
+// external/cityhash/cityhash.cpp:238-266 (CityMurmur, len <= 16 branch), :116-125 (HashLen0to16),
+// cityhash.hpp:90-99 (Hash128to64).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t city_h16(uint64_t u, uint64_t v) {
+    const uint64_t kMul = 0x9ddfea08eb382d69ull;
+    uint64_t a = (u ^ v) * kMul; a ^= (a >> 47);
+    uint64_t b = (v ^ a) * kMul; b ^= (b >> 47);
+    return b * kMul;
+}
+struct Hash128 { uint64_t first, second; };
+
+__device__ __forceinline__ Hash128 city_tail(const DevPhf& f, uint64_t h, uint64_t key_lo) {
+    uint64_t a = f.city_a;
+    uint64_t c = f.city_cb + h;
+    uint64_t d = a + key_lo; d ^= (d >> 47);
+    a = city_h16(a, c);
+    uint64_t b = city_h16(d, f.seed_hi);
+    return {a ^ b, city_h16(b, a)};
+}
+__device__ __forceinline__ Hash128 city_hash_u64(const DevPhf& f, uint64_t key) {          // len = 8
+    return city_tail(f, city_h16(8 + ((key & 0xffffffffull) << 3), key >> 32), key);
+}
+__device__ __forceinline__ Hash128 city_hash_u128(const DevPhf& f, uint64_t lo, uint64_t hi) {  // len = 16
+    uint64_t t = hi + 16;
+    uint64_t rot = (t >> 16) | (t << 48);
+    return city_tail(f, city_h16(lo, rot) ^ hi, lo);
+}
+
+// partitioned_phf::position (partitioned_phf.hpp:145-149) -> single_phf::position
+// (single_phf.hpp:68-78) with opt_bucketer::bucket (utils/bucketers.hpp:38-39), range_bucketer
+// (:129-131), compact pilots (utils/encoders.hpp:33-35), mix (utils/hasher.hpp:41-43) and the
+// minimal remap through the (decoded) free slots.
+__device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const DevPhf& f, Hash128 h) {
+    uint64_t part = 0;
+    if (f.num_partitions > 1) part = (((h.first ^ h.second) >> 32) * f.num_partitions) >> 32;
+    const DevPhfPart* __restrict__ p = f.parts + part;
+    const uint64_t h1 = h.first;
+    uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
+    uint64_t bucket = __umul64hi(H, p->num_buckets);
+    uint64_t pilot = compact_get(ix.pilots + p->pilots_word, p->pilot_width, p->pilot_mask, bucket);
+    uint64_t pos = __umul64hi((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, p->table_size);
+    if (pos >= p->num_keys) pos = __ldg(ix.free_slots + p->free_off + (pos - p->num_keys));
+    return p->offset + pos;
+}
+
+// ------------------------------------------------------------------------------------------------
+// string end-points: decoded_offsets::offset_to_id (include/offsets.hpp:138-154) ->
+// endpoints_sequence::locate (endpoints_sequence.hpp:182-198).  Returns the index of the largest
+// end-point <= x; begin/end are that end-point and the next.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_t x, uint64_t& begin, uint64_t& end) {
+    // ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none): ends[i] <= x holds
+    uint64_t i = __ldg(ix.ends_dir + (x >> ix.dir_shift));
+    uint64_t cur = __ldg(ix.ends + i), next = __ldg(ix.ends + i + 1);
+    // advance to the last end-point <= x; at most (1 << dir_shift) / k + 1 steps
+    while (next <= x) { cur = next; ++i; next = __ldg(ix.ends + i + 1); }
+    begin = cur; end = next;
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one lookup
+// ------------------------------------------------------------------------------------------------
+struct LookupResult {          // include/util.hpp:38-62
+    uint64_t kmer_id, kmer_id_in_string, kmer_offset;
+    int64_t kmer_orientation;
+    uint64_t string_id, string_begin, string_end, minimizer_found;
+};
+
+__device__ __forceinline__ void result_clear(LookupResult& r, bool minimizer_found) {
+    r.kmer_id = r.kmer_id_in_string = r.kmer_offset = ~0ull;
+    r.kmer_orientation = 1;
+    r.string_id = r.string_begin = r.string_end = ~0ull;
+    r.minimizer_found = minimizer_found ? 1 : 0;
+}
+
+// kmers_city_hasher_128::hash, include/hash_util.hpp:59-67: the key is sizeof(x.bits) = 8 or 16 bytes
+__device__ __forceinline__ Hash128 skew_hash(const DevPhf& f, Kmer<1> x) { return city_hash_u64(f, x.lo); }
+__device__ __forceinline__ Hash128 skew_hash(const DevPhf& f, Kmer<2> x) { return city_hash_u128(f, x.lo, x.hi); }
+
+// sparse_and_skew_index::lookup (sparse_and_skew_index.hpp:112-137): minimizer -> bucket.
+// Returns the number of offsets in the bucket; `first` = the single offset (SINGLETON/HEAVYLOAD)
+// or the index of the first entry in mid_load_buckets (MIDLOAD).
+template <int W>
+__device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t minimizer, Kmer<W> skew_key,
+                                              uint64_t& first, bool& heavy) {
+    uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
+    uint64_t code = compact_get(ix.codewords, id);
+    heavy = false;
+    if ((code & 1) == 0) { first = code >> 1; return 1; }                         // SINGLETON
+    if ((code & 3) == 1) {                                                        // MIDLOAD
+        code >>= 2;
+        uint32_t size = (uint32_t)(code & 63) + 2;
+        first = ix.begin_buckets_of_size[size] + (code >> 6) * size;
+        return size;
+    }
+    // HEAVYLOAD: skew_index::lookup, sparse_and_skew_index.hpp:34-44
+    code >>= 2;
+    uint32_t part = (uint32_t)code & 7;
+    uint64_t begin = code >> 3;
+    uint64_t kid = phf_position(ix, ix.skew[part], skew_hash(ix.skew[part], skew_key));
+    uint64_t pos_in_bucket = compact_get(ix.skew_pos[part], kid);
+    uint64_t idx = begin + pos_in_bucket;
+    // A k-mer that was never a key gets an arbitrary slot; the reference then reads past the bucket
+    // (spss.hpp:51-63).  Whatever is read cannot make the k-mer comparison succeed for an absent
+    // k-mer, so clamping yields the same answer without the out-of-bounds access.
+    if (idx >= ix.heavy.size) idx = ix.heavy.size - 1;
+    first = compact_get(ix.heavy, idx);
+    heavy = true;
+    return 1;
+}
+
+// Regular pass: dictionary::lookup_regular (src/dictionary.cpp:7-22) + spss::lookup_regular
+// (spectrum_preserving_string_set.hpp:29-73, _lookup_regular :213-235).
+// FULL = also produce minimizer_found exactly (needs the m-mer check of spss.hpp:46-65); without
+// it the k-mer comparison alone decides, which yields the same ids (a k-mer match implies the
+// m-mer match because the minimizer is a substring of the k-mer at pos_in_kmer).
+template <int W, bool FULL>
+__device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
+    const uint32_t k = ix.k, m = ix.m;
+    Minimizer mi = compute_minimizer(x, k, m, ix.magic);
+    uint64_t first; bool heavy;
+    uint32_t n = bucket_of<W>(ix, mi.value, x, first, heavy);
+    uint64_t off0 = (n == 1) ? first : compact_get(ix.mid_load, first);
+    if (FULL) {
+        if (read_mmer(ix, off0, m) != mi.value) { result_clear(res, heavy); return false; }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t off = (i == 0) ? off0 : compact_get(ix.mid_load, first + i);
+        if (off < mi.pos) continue;
+        uint64_t ko = off - mi.pos;
+        if (!kmer_eq(read_kmer(ix, ko, k, (Kmer<W>*)nullptr), x)) continue;
+        uint64_t sb, se;
+        uint64_t sid = locate_string(ix, ko, sb, se);
+        if (ko < se - k + 1) {                          // spss.hpp:233: reject k-mers spanning two strings
+            res.kmer_id = ko - sid * (k - 1);
+            res.kmer_id_in_string = ko - sb;
+            res.kmer_offset = ko;
+            res.kmer_orientation = 1;
+            res.string_id = sid; res.string_begin = sb; res.string_end = se;
+            res.minimizer_found = 1;
+            return true;
+        }
+    }
+    result_clear(res, true);
+    return false;
+}
+
+// Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)
+// + spss::lookup_canonical (spss.hpp:75-112, _lookup_canonical :237-247, __lookup_canonical :249-275)
+template <int W, bool FULL>
+__device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kmer<W> x, Kmer<W> xr, Minimizer mi,
+                                                      LookupResult& res) {
+    const uint32_t k = ix.k, m = ix.m;
+    Kmer<W> canon = kmer_lt(x, xr) ? x : xr;            // std::min(uint_kmer, uint_kmer_rc), dictionary.cpp:53
+    uint64_t first; bool heavy;
+    uint32_t n = bucket_of<W>(ix, mi.value, canon, first, heavy);
+    uint64_t off0 = (n == 1) ? first : compact_get(ix.mid_load, first);
+    if (FULL) {
+        uint64_t rm = read_mmer(ix, off0, m);
+        if (rm != mi.value && rm != mmer_rc(mi.value, m)) { result_clear(res, heavy); return false; }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t off = (i == 0) ? off0 : compact_get(ix.mid_load, first + i);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            uint32_t p = t == 0 ? mi.pos : k - m - mi.pos;
+            if (off < p) continue;
+            uint64_t ko = off - p;
+            Kmer<W> r = read_kmer(ix, ko, k, (Kmer<W>*)nullptr);
+            bool eq_f = kmer_eq(r, x), eq_r = kmer_eq(r, xr);
+            if (!eq_f && !eq_r) continue;
+            uint64_t sb, se;
+            uint64_t sid = locate_string(ix, ko, sb, se);
+            if (ko < se - k + 1) {
+                res.kmer_id = ko - sid * (k - 1);
+                res.kmer_id_in_string = ko - sb;
+                res.kmer_offset = ko;
+                res.kmer_orientation = eq_r ? -1 : 1;   // spss.hpp:263-264 (rc wins when both equal: impossible for odd k)
+                res.string_id = sid; res.string_begin = sb; res.string_end = se;
+                res.minimizer_found = 1;
+                return true;
+            }
+        }
+    }
+    result_clear(res, true);
+    return false;
+}
+
+// dictionary::lookup(Kmer, check_reverse_complement), src/dictionary.cpp:64-78 (+ :24-42)
+template <int W, bool FULL>
+__device__ __forceinline__ void lookup_kmer(const DeviceIndex& ix, Kmer<W> x, bool check_rc, LookupResult& res) {
+    const uint32_t k = ix.k;
+    if (ix.canonical) {
+        Kmer<W> xr = kmer_rc(x, k);
+        Minimizer mf = compute_minimizer(x, k, ix.m, ix.magic);
+        Minimizer mr = compute_minimizer(xr, k, ix.m, ix.magic);
+        if (mf.value < mr.value) { lookup_canonical_with<W, FULL>(ix, x, xr, mf, res); }
+        else if (mr.value < mf.value) { lookup_canonical_with<W, FULL>(ix, x, xr, mr, res); }
+        else {
+            if (!lookup_canonical_with<W, FULL>(ix, x, xr, mf, res)) lookup_canonical_with<W, FULL>(ix, x, xr, mr, res);
+        }
+        return;
+    }
+    if (lookup_regular<W, FULL>(ix, x, res)) return;
+    if (check_rc) {
+        lookup_regular<W, FULL>(ix, kmer_rc(x, k), res);
+        res.kmer_orientation = -1;                      // dictionary.cpp:74-75: also for a miss
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sshash_b200

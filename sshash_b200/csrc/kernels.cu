@@ -1,0 +1,435 @@
+// kernels.cu -- sm_100a kernels of the lookup path and their launchers.
+//
+// All kernels are integer / indexing work bound by random 32-byte-sector accesses to the index
+// arrays (L2 when the index fits its 126 MB, HBM otherwise); there is nothing GEMM-shaped here,
+// so no tensor cores.  Parallelisation: one THREAD per query k-mer -- a lookup is a chain of 4-6
+// dependent loads, and the only way to cover ~600-800 ns of HBM latency per link is to keep tens
+// of thousands of independent chains in flight (148 SMs x up to 2048 threads).
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+
+namespace sshash_b200 {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+template <int W>
+__device__ __forceinline__ Kmer<W> load_kmer(const uint64_t* __restrict__ kmers, uint64_t i);
+template <>
+__device__ __forceinline__ Kmer<1> load_kmer<1>(const uint64_t* __restrict__ kmers, uint64_t i) {
+    return {__ldcs(kmers + i)};
+}
+template <>
+__device__ __forceinline__ Kmer<2> load_kmer<2>(const uint64_t* __restrict__ kmers, uint64_t i) {
+    ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(kmers) + i);
+    return {v.x, v.y};
+}
+__device__ __forceinline__ void store_kmer(uint64_t* out, uint64_t i, Kmer<1> x) { __stcs(out + i, x.lo); }
+__device__ __forceinline__ void store_kmer(uint64_t* out, uint64_t i, Kmer<2> x) {
+    __stcs(reinterpret_cast<ulonglong2*>(out) + i, make_ulonglong2(x.lo, x.hi));
+}
+
+__device__ __forceinline__ void store_full(sshash_lookup_result* full, uint64_t i, const LookupResult& r) {
+    // 64-byte record written as four 16-byte streaming stores
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(full + i);
+    __stcs(p + 0, make_ulonglong2(r.kmer_id, r.kmer_id_in_string));
+    __stcs(p + 1, make_ulonglong2(r.kmer_offset, (uint64_t)r.kmer_orientation));
+    __stcs(p + 2, make_ulonglong2(r.string_id, r.string_begin));
+    __stcs(p + 3, make_ulonglong2(r.string_end, r.minimizer_found));
+}
+
+// util::string_to_uint_kmer (include/util.hpp:207-213) with char_to_uint = (c >> 1) & 3
+// (include/kmer.hpp:194); no validation, exactly like the reference.
+template <int W>
+__device__ __forceinline__ Kmer<W> pack_ascii(const char* __restrict__ s, uint32_t k);
+template <>
+__device__ __forceinline__ Kmer<1> pack_ascii<1>(const char* __restrict__ s, uint32_t k) {
+    uint64_t x = 0;
+    for (uint32_t i = 0; i < k; ++i) x |= (uint64_t)(((uint8_t)s[i] >> 1) & 3) << (2 * i);
+    return {x};
+}
+template <>
+__device__ __forceinline__ Kmer<2> pack_ascii<2>(const char* __restrict__ s, uint32_t k) {
+    uint64_t lo = 0, hi = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        uint64_t c = ((uint8_t)s[i] >> 1) & 3;
+        if (i < 32) lo |= c << (2 * i); else hi |= c << (2 * (i - 32));
+    }
+    return {lo, hi};
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched dictionary::lookup.  MODE 0: ids, 1: ids + full records, 2: membership bytes
+// ------------------------------------------------------------------------------------------------
+template <int W, int MODE, bool ASCII>
+__global__ void __launch_bounds__(kBlock)
+lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
+              uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Kmer<W> x;
+        if (ASCII) x = pack_ascii<W>(static_cast<const char*>(queries) + i * ix.k, ix.k);
+        else x = load_kmer<W>(static_cast<const uint64_t*>(queries), i);
+        LookupResult r;
+        lookup_kmer<W, MODE == 1>(ix, x, check_rc != 0, r);
+        if (MODE == 2) member[i] = r.kmer_id != ~0ull;
+        else {
+            if (ids) __stcs(ids + i, r.kmer_id);
+            if (MODE == 1) store_full(full, i, r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched dictionary::access: offsets::id_to_offset (include/offsets.hpp:41-65) restated as a
+// binary search over the decoded end-points for the last string whose first k-mer id
+// (= begin - string_id * (k-1)) is <= id, then spss::access (spss.hpp:114-118).
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kBlock)
+access_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ ids, uint64_t n,
+              uint64_t* __restrict__ kmers_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t km1 = ix.k - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t id = __ldcs(ids + i);
+        uint64_t lo = 0, hi = ix.n_ends - 1;
+        while (hi - lo > 1) {
+            uint64_t mid = lo + (hi - lo) / 2;
+            if (__ldg(ix.ends + mid) - mid * km1 <= id) lo = mid; else hi = mid;
+        }
+        store_kmer(kmers_out, i, read_kmer(ix, id + lo * km1, ix.k, (Kmer<W>*)nullptr));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming membership, step 1: one independent lookup per window.  The reference defines every
+// streamed result as equal to dict->lookup(kmer) (include/streaming_query.hpp:107), which is what
+// makes the windows independent.  One WARP per read; lanes stride over the read's windows so the
+// character loads of neighbouring windows hit the same L1 lines.
+// Window record: id (u64) + string_id (low 62 bits) | flags (bit 63: backward, bit 62: valid)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool valid_base(uint8_t c) {  // canonicalize_basepair_forward_map, kmer.hpp:209-219
+    uint8_t u = c & 0xDF;
+    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBlock)
+stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
+                      const uint64_t* __restrict__ read_offsets, const uint64_t* __restrict__ win_offsets,
+                      uint64_t num_reads, uint64_t* __restrict__ win_id, uint64_t* __restrict__ win_aux) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t k = ix.k;
+    for (uint64_t r = warp; r < num_reads; r += nwarps) {
+        const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
+        if (len < k) continue;
+        const uint64_t nwin = len - k + 1, w0 = win_offsets[r];
+        for (uint64_t i = lane; i < nwin; i += 32) {
+            const char* s = bases + b + i;
+            bool valid = true;
+            for (uint32_t j = 0; j < k; ++j) valid &= valid_base((uint8_t)s[j]);
+            uint64_t id = ~0ull, aux = 0;
+            if (valid) {
+                LookupResult res;
+                lookup_kmer<W, false>(ix, pack_ascii<W>(s, k), true, res);
+                id = res.kmer_id;
+                aux = (1ull << 62) | (res.string_id & ((1ull << 62) - 1)) | (res.kmer_orientation < 0 ? (1ull << 63) : 0);
+            }
+            win_id[w0 + i] = id;
+            win_aux[w0 + i] = aux;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming membership, step 2: the reference's per-read state machine
+// (include/streaming_query.hpp:56-197) replayed over the window records by one THREAD per read to
+// produce the searches / extensions / negative / invalid counters and the streamed ids.  A window
+// is an EXTENSION when the previous window left `remaining > 0` and the next k-mer of the string
+// (read through a literal restatement of kmer_iterator, include/kmer_iterator.hpp:8-86) equals the
+// window's k-mer or its reverse complement; otherwise it is a seed(): positive -> SEARCH.
+// The restated iterator keeps the reference's word order in fill_buff_reverse (:72-79), which for
+// the 128-bit k-mer type swaps the two halves: in a max_k = 63 build backward extensions therefore
+// (almost) never match and are counted as searches, exactly as the reference does.
+// ------------------------------------------------------------------------------------------------
+template <int W> struct KmerIter;
+template <> struct KmerIter<1> {
+    uint64_t pos, avail, buff;
+    __device__ void at(uint64_t p) { pos = p; avail = 0; buff = 0; }
+    __device__ uint64_t word(const DeviceIndex& ix, uint64_t p) const { return read_word64(ix.strings, p); }
+    __device__ void fill(const DeviceIndex& ix) { buff = word(ix, pos); avail = 64; }
+    __device__ void fill_reverse(const DeviceIndex& ix) {
+        buff = word(ix, (pos > 64 ? pos : 64) - 64);
+        avail = pos < 64 ? pos : 64;
+        uint64_t pad = 64 - avail;
+        buff = pad >= 64 ? 0 : buff << pad;
+    }
+    __device__ Kmer<1> get(const DeviceIndex& ix) { if (avail < 2 * ix.k) fill(ix); return {buff & low_mask(2 * ix.k)}; }
+    __device__ Kmer<1> get_reverse(const DeviceIndex& ix) { if (avail < 2 * ix.k) fill_reverse(ix); return {buff >> (64 - 2 * ix.k)}; }
+    __device__ void next(const DeviceIndex& ix) { if (avail < 2) fill(ix); buff >>= 2; avail -= 2; pos += 2; }
+    __device__ void next_reverse(const DeviceIndex& ix) { if (avail < 2) fill_reverse(ix); buff <<= 2; avail -= 2; pos -= 2; }
+};
+template <> struct KmerIter<2> {
+    uint64_t pos, avail, lo, hi;  // buff = hi:lo
+    __device__ void at(uint64_t p) { pos = p; avail = 0; lo = hi = 0; }
+    __device__ uint64_t word(const DeviceIndex& ix, uint64_t p) const { return read_word64(ix.strings, p); }
+    __device__ void fill(const DeviceIndex& ix) { hi = word(ix, pos + 64); lo = word(ix, pos); avail = 128; }
+    __device__ void fill_reverse(const DeviceIndex& ix) {
+        uint64_t base = pos > 128 ? pos : 128;
+        hi = word(ix, base - 128);  // appended first -> ends up in the HIGH half (reference quirk)
+        lo = word(ix, base - 64);
+        avail = pos < 128 ? pos : 128;
+        uint64_t pad = 128 - avail;
+        if (pad >= 128) { lo = hi = 0; }
+        else if (pad >= 64) { hi = lo << (pad - 64); lo = 0; }
+        else if (pad) { hi = (hi << pad) | (lo >> (64 - pad)); lo <<= pad; }
+    }
+    __device__ Kmer<2> get(const DeviceIndex& ix) {
+        if (avail < 2 * ix.k) fill(ix);
+        uint32_t b = 2 * ix.k;
+        return b <= 64 ? Kmer<2>{lo & low_mask(b), 0} : Kmer<2>{lo, hi & low_mask(b - 64)};
+    }
+    __device__ Kmer<2> get_reverse(const DeviceIndex& ix) {
+        if (avail < 2 * ix.k) fill_reverse(ix);
+        uint32_t s = 128 - 2 * ix.k;  // >= 2
+        return s >= 64 ? Kmer<2>{hi >> (s - 64), 0} : Kmer<2>{(lo >> s) | (hi << (64 - s)), hi >> s};
+    }
+    __device__ void next(const DeviceIndex& ix) {
+        if (avail < 2) fill(ix);
+        lo = (lo >> 2) | (hi << 62); hi >>= 2; avail -= 2; pos += 2;
+    }
+    __device__ void next_reverse(const DeviceIndex& ix) {
+        if (avail < 2) fill_reverse(ix);
+        hi = (hi << 2) | (lo >> 62); lo <<= 2; avail -= 2; pos -= 2;
+    }
+};
+
+template <int W>
+__global__ void __launch_bounds__(kBlock)
+stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
+                   const uint64_t* __restrict__ read_offsets, const uint64_t* __restrict__ win_offsets,
+                   uint64_t num_reads, const uint64_t* __restrict__ win_id, const uint64_t* __restrict__ win_aux,
+                   uint64_t* __restrict__ ids_out, unsigned long long* __restrict__ counters) {
+    const uint32_t k = ix.k;
+    unsigned long long n_search = 0, n_ext = 0, n_neg = 0, n_inv = 0, n_kmers = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_reads; r += stride) {
+        const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
+        if (len < k) continue;
+        const uint64_t nwin = len - k + 1, w0 = win_offsets[r];
+        n_kmers += nwin;
+        uint64_t remaining = 0, cur_id = ~0ull;
+        bool backward = false;
+        KmerIter<W> it; it.at(0);
+        for (uint64_t i = 0; i < nwin; ++i) {
+            const uint64_t aux = win_aux[w0 + i];
+            if (!(aux >> 62 & 1)) {                      // invalid window: reset() (streaming_query.hpp:59-65)
+                n_inv += 1; remaining = 0; cur_id = ~0ull;
+                if (ids_out) ids_out[w0 + i] = ~0ull;
+                continue;
+            }
+            bool extended = false;
+            if (remaining != 0) {                        // :88-99
+                Kmer<W> x = pack_ascii<W>(bases + b + i, k), xr = kmer_rc(x, k), e;
+                if (!backward) { it.next(ix); e = it.get(ix); }
+                else { it.next_reverse(ix); e = it.get_reverse(ix); }
+                if (kmer_eq(e, x) || kmer_eq(e, xr)) {
+                    n_ext += 1;
+                    cur_id += backward ? ~0ull : 1ull;   // kmer_id += orientation
+                    remaining -= 1;
+                    extended = true;
+                }
+            }
+            if (!extended) {                             // seed() :144-197
+                remaining = 0;
+                cur_id = win_id[w0 + i];
+                if (cur_id == ~0ull) { n_neg += 1; }
+                else {
+                    n_search += 1;
+                    backward = (aux >> 63) != 0;
+                    const uint64_t sid = aux & ((1ull << 62) - 1);
+                    const uint64_t sb = __ldg(ix.ends + sid), se = __ldg(ix.ends + sid + 1);
+                    const uint64_t ko = cur_id + sid * (k - 1);          // kmer_offset in bases
+                    const uint64_t in_string = ko - sb;
+                    uint64_t bitpos = 2 * ko;
+                    remaining = (se - sb - k) - in_string;
+                    if (backward) { bitpos += 2 * k; remaining = in_string; }
+                    it.at(bitpos);
+                }
+            }
+            if (ids_out) ids_out[w0 + i] = cur_id;
+        }
+    }
+    // block reduction -> 5 atomics per block
+    __shared__ unsigned long long sh[5];
+    if (threadIdx.x < 5) sh[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long v[5] = {n_kmers, n_search, n_ext, n_neg, n_inv};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        unsigned long long x = v[j];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&sh[j], x);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && sh[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sh[threadIdx.x]);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// win_offsets = exclusive prefix sum of max(0, len_r - k + 1) over the reads (three small kernels:
+// per-block totals, a single-block scan of the totals, per-block exclusive scan + offset).
+// win_offsets has num_reads + 1 entries; the last one is the total number of windows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanItems = 8;                       // reads per thread
+constexpr int kScanTile = kBlock * kScanItems;      // reads per block
+
+__device__ __forceinline__ uint64_t windows_of(const uint64_t* __restrict__ ro, uint64_t r, uint64_t num_reads, uint32_t k) {
+    if (r >= num_reads) return 0;
+    uint64_t len = ro[r + 1] - ro[r];
+    return len >= k ? len - k + 1 : 0;
+}
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t& total) {
+    __shared__ uint64_t warp_sums[kBlock / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = lane < kBlock / 32 ? warp_sums[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < kBlock / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint64_t base = wid ? warp_sums[wid - 1] : 0;
+    total = warp_sums[kBlock / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+win_block_sums_kernel(uint32_t k, const uint64_t* __restrict__ ro, uint64_t num_reads, uint64_t* __restrict__ block_sums) {
+    uint64_t r0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems, s = 0;
+    for (int j = 0; j < kScanItems; ++j) s += windows_of(ro, r0 + j, num_reads, k);
+    uint64_t total;
+    block_exclusive_scan(s, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kBlock)
+win_scan_sums_kernel(uint64_t* __restrict__ block_sums, uint64_t nblocks) {   // single block
+    uint64_t carry = 0;
+    for (uint64_t b0 = 0; b0 < nblocks; b0 += kBlock) {
+        uint64_t i = b0 + threadIdx.x;
+        uint64_t v = i < nblocks ? block_sums[i] : 0, total;
+        uint64_t ex = block_exclusive_scan(v, total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+win_offsets_kernel(uint32_t k, const uint64_t* __restrict__ ro, uint64_t num_reads, const uint64_t* __restrict__ block_sums,
+                   uint64_t* __restrict__ win_offsets) {
+    uint64_t r0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems, s = 0;
+    uint64_t c[kScanItems];
+    for (int j = 0; j < kScanItems; ++j) { c[j] = windows_of(ro, r0 + j, num_reads, k); s += c[j]; }
+    uint64_t total;
+    uint64_t off = block_sums[blockIdx.x] + block_exclusive_scan(s, total);
+    for (int j = 0; j < kScanItems; ++j) {
+        if (r0 + j <= num_reads) win_offsets[r0 + j] = off;   // entry num_reads = grand total
+        off += c[j];
+    }
+}
+
+std::atomic<uint64_t> g_launches{0};
+
+inline int grid_for(uint64_t n, int sm_count, int blocks_per_sm) {
+    uint64_t need = (n + kBlock - 1) / kBlock;
+    uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace
+
+uint64_t kernel_launch_count() { return g_launches.load(); }
+
+cudaError_t launch_lookup(const DeviceIndex& ix, int sm_count, const void* queries, bool ascii, uint64_t n, bool check_rc,
+                          uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(n, sm_count, 8);
+    const int mode = member ? 2 : (full ? 1 : 0);
+    const int crc = check_rc ? 1 : 0;
+#define SSHASH_LAUNCH(W, MODE, ASCII) \
+    lookup_kernel<W, MODE, ASCII><<<grid, kBlock, 0, stream>>>(ix, queries, n, crc, ids, full, member)
+#define SSHASH_DISPATCH_MODE(W, ASCII)                     \
+    do {                                                   \
+        if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);         \
+        else if (mode == 1) SSHASH_LAUNCH(W, 1, ASCII);    \
+        else SSHASH_LAUNCH(W, 2, ASCII);                   \
+    } while (0)
+    if (ix.kmer_words == 1) { if (ascii) SSHASH_DISPATCH_MODE(1, true); else SSHASH_DISPATCH_MODE(1, false); }
+    else { if (ascii) SSHASH_DISPATCH_MODE(2, true); else SSHASH_DISPATCH_MODE(2, false); }
+#undef SSHASH_DISPATCH_MODE
+#undef SSHASH_LAUNCH
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_access(const DeviceIndex& ix, int sm_count, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
+                          cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(n, sm_count, 8);
+    if (ix.kmer_words == 1) access_kernel<1><<<grid, kBlock, 0, stream>>>(ix, ids, n, kmers_out);
+    else access_kernel<2><<<grid, kBlock, 0, stream>>>(ix, ids, n, kmers_out);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+uint64_t window_offsets_scratch_words(uint64_t num_reads) { return (num_reads + 1 + kScanTile - 1) / kScanTile + 1; }
+
+cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
+                                  uint64_t* block_sums, cudaStream_t stream) {
+    const uint64_t nblocks = (num_reads + 1 + kScanTile - 1) / kScanTile;
+    win_block_sums_kernel<<<(unsigned)nblocks, kBlock, 0, stream>>>(k, read_offsets, num_reads, block_sums);
+    win_scan_sums_kernel<<<1, kBlock, 0, stream>>>(block_sums, nblocks);
+    win_offsets_kernel<<<(unsigned)nblocks, kBlock, 0, stream>>>(k, read_offsets, num_reads, block_sums, win_offsets);
+    g_launches.fetch_add(3);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_streaming(const DeviceIndex& ix, int sm_count, const char* bases, const uint64_t* read_offsets,
+                             const uint64_t* win_offsets, uint64_t num_reads, uint64_t* win_id, uint64_t* win_aux,
+                             uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream) {
+    if (num_reads == 0) return cudaSuccess;
+    {
+        uint64_t threads = num_reads * 32;
+        const int grid = grid_for(threads, sm_count, 8);
+        if (ix.kmer_words == 1)
+            stream_windows_kernel<1><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
+        else
+            stream_windows_kernel<2><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
+        g_launches.fetch_add(1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    {
+        const int grid = grid_for(num_reads, sm_count, 8);
+        if (ix.kmer_words == 1)
+            stream_scan_kernel<1><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
+        else
+            stream_scan_kernel<2><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
+        g_launches.fetch_add(1);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sshash_b200

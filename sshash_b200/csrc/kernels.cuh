@@ -1,0 +1,36 @@
+// kernels.cuh -- launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/sshash_gpu.h"
+#include "device_index.cuh"
+
+namespace sshash_b200 {
+
+// number of kernels launched by this library since it was loaded (bench.py's `gpu_launches`)
+uint64_t kernel_launch_count();
+
+// Batched dictionary::lookup.  `queries`: packed k-mers (ascii = false) or n*k characters.
+// Exactly one of {ids and/or full, member} is produced; all pointers are DEVICE pointers.
+cudaError_t launch_lookup(const DeviceIndex& ix, int sm_count, const void* queries, bool ascii, uint64_t n, bool check_rc,
+                          uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream);
+
+cudaError_t launch_access(const DeviceIndex& ix, int sm_count, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
+                          cudaStream_t stream);
+
+// win_offsets[r] = number of windows in reads [0, r), computed on the device from read_offsets
+cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
+                                  uint64_t* block_sums, cudaStream_t stream);
+uint64_t window_offsets_scratch_words(uint64_t num_reads);
+
+// Streaming membership over a batch of reads: per-window lookups, then the per-read replay of the
+// reference state machine.  counters[5] += {num_kmers, searches, extensions, negative, invalid}.
+cudaError_t launch_streaming(const DeviceIndex& ix, int sm_count, const char* bases, const uint64_t* read_offsets,
+                             const uint64_t* win_offsets, uint64_t num_reads, uint64_t* win_id, uint64_t* win_aux,
+                             uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream);
+
+}  // namespace sshash_b200

@@ -1,0 +1,217 @@
+"""Python mirror of the reference's `dictionary<Kmer, Offsets>` for the lookup path.
+
+Same method names and argument meaning as the reference class (include/dictionary.hpp:10-181):
+`k() m() canonical() num_kmers() num_strings() weighted()`, `lookup`, `is_member`, `access`,
+`streaming_query_from_file`, plus the batched forms every caller of the reference loops to get
+(tools/perf.hpp:55-60, test/check.hpp:29-31).  Everything executes in the CUDA library through the
+C ABI (include/sshash_gpu.h); numpy arrays are host buffers, torch CUDA tensors are used in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import Info, LookupResult, StreamingReport, SshashGpuError, check  # noqa: F401
+
+INVALID = np.uint64(2**64 - 1)  # constants::invalid_uint64, include/constants.hpp:5
+
+RESULT_DTYPE = np.dtype([("kmer_id", "<u8"), ("kmer_id_in_string", "<u8"), ("kmer_offset", "<u8"),
+                         ("kmer_orientation", "<i8"), ("string_id", "<u8"), ("string_begin", "<u8"),
+                         ("string_end", "<u8"), ("minimizer_found", "<u8")])
+
+_NUC = {"A": 0, "C": 1, "T": 2, "G": 3}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x) -> int:
+    if x is None:
+        return 0
+    if _is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+def string_to_uint_kmer(s: str) -> int:
+    """util::string_to_uint_kmer (include/util.hpp:207-213): (c >> 1) & 3, base 0 in the low bits."""
+    x = 0
+    for i, c in enumerate(s.encode()):
+        x |= ((c >> 1) & 3) << (2 * i)
+    return x
+
+
+def uint_kmer_to_string(x: int, k: int) -> str:
+    return "".join("ACTG"[(x >> (2 * i)) & 3] for i in range(k))
+
+
+class Dictionary:
+    """An SSHash index resident in the HBM of one GPU."""
+
+    def __init__(self, index_filename: str, device: int = 0, max_k: int = 0):
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        check(self._lib.sshash_gpu_open(index_filename.encode(), device, max_k, C.byref(self._h)))
+        info = Info()
+        check(self._lib.sshash_gpu_info(self._h, C.byref(info)))
+        self.info = {n: int(getattr(info, n)) for n, _ in Info._fields_}
+        self.words = 1 if self.info["max_k"] == 31 else 2
+        self.device = device
+
+    # ---- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sshash_gpu_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- accessors, include/dictionary.hpp:31-38 ----------------------------------------------
+    def k(self) -> int: return self.info["k"]
+    def m(self) -> int: return self.info["m"]
+    def canonical(self) -> bool: return bool(self.info["canonical"])
+    def weighted(self) -> bool: return bool(self.info["weighted"])
+    def num_kmers(self) -> int: return self.info["num_kmers"]
+    def num_strings(self) -> int: return self.info["num_strings"]
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _count(self, kmers) -> int:
+        n = kmers.numel() if _is_torch(kmers) else kmers.size
+        if n % self.words:
+            raise ValueError("packed k-mer buffer length must be a multiple of %d words" % self.words)
+        return n // self.words
+
+    def _prep_in(self, a, dtype=np.uint64):
+        if _is_torch(a):
+            if not a.is_contiguous():
+                a = a.contiguous()
+            return a
+        return np.ascontiguousarray(a, dtype=dtype)
+
+    def _alloc_like(self, ref, n, dtype, shape=None):
+        shape = (n,) if shape is None else shape
+        if _is_torch(ref):
+            import torch
+            tdt = {np.uint64: torch.int64, np.uint8: torch.uint8}[dtype]
+            return torch.empty(shape, dtype=tdt, device=ref.device)
+        return np.empty(shape, dtype=dtype)
+
+    # ---- lookup, include/dictionary.hpp:41-42 -------------------------------------------------
+    def lookup_batch(self, kmers, check_reverse_complement: bool = True, out=None, full: bool = False,
+                     stream: int = 0):
+        """Batched dictionary::lookup(Kmer, bool).  kmers: uint64 array (numpy = host, torch CUDA
+        tensor = device), `words` words per k-mer.  Returns kmer ids (uint64; torch: int64 bit
+        patterns) or, with full=True, a structured array of complete lookup_result records."""
+        kmers = self._prep_in(kmers)
+        n = self._count(kmers)
+        if full:
+            if _is_torch(kmers):
+                import torch
+                res = torch.empty((n, 8), dtype=torch.int64, device=kmers.device)
+            else:
+                res = np.empty(n, dtype=RESULT_DTYPE)
+            check(self._lib.sshash_gpu_lookup_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), None,
+                                                    _ptr(res), stream))
+            return res
+        ids = out if out is not None else self._alloc_like(kmers, n, np.uint64)
+        check(self._lib.sshash_gpu_lookup_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(ids),
+                                                None, stream))
+        return ids
+
+    def lookup_batch_ascii(self, strings: bytes, check_reverse_complement: bool = True, full: bool = False):
+        """Batched dictionary::lookup(char const*, bool): n*k characters, no validation."""
+        buf = np.frombuffer(strings, dtype=np.uint8)
+        if buf.size % self.k():
+            raise ValueError("ASCII buffer length must be a multiple of k")
+        n = buf.size // self.k()
+        if full:
+            res = np.empty(n, dtype=RESULT_DTYPE)
+            check(self._lib.sshash_gpu_lookup_batch_ascii(self._h, _ptr(buf), n, int(check_reverse_complement), None,
+                                                          _ptr(res), None))
+            return res
+        ids = np.empty(n, dtype=np.uint64)
+        check(self._lib.sshash_gpu_lookup_batch_ascii(self._h, _ptr(buf), n, int(check_reverse_complement), _ptr(ids),
+                                                      None, None))
+        return ids
+
+    def lookup(self, kmer, check_reverse_complement: bool = True) -> dict:
+        """Scalar dictionary::lookup (string or packed int) -> lookup_result as a dict."""
+        if isinstance(kmer, str):
+            if len(kmer) != self.k():
+                raise ValueError("k-mer string must have length k")
+            kmer = string_to_uint_kmer(kmer)
+        q = np.array([(kmer >> (64 * i)) & (2**64 - 1) for i in range(self.words)], dtype=np.uint64)
+        r = self.lookup_batch(q, check_reverse_complement, full=True)[0]
+        return {n: int(r[n]) for n in RESULT_DTYPE.names}
+
+    # ---- membership, include/dictionary.hpp:75-76 ---------------------------------------------
+    def is_member_batch(self, kmers, check_reverse_complement: bool = True, stream: int = 0):
+        kmers = self._prep_in(kmers)
+        n = self._count(kmers)
+        out = self._alloc_like(kmers, n, np.uint8)
+        check(self._lib.sshash_gpu_is_member_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(out),
+                                                   stream))
+        return out if _is_torch(out) else out.astype(bool)
+
+    def is_member(self, kmer, check_reverse_complement: bool = True) -> bool:
+        return self.lookup(kmer, check_reverse_complement)["kmer_id"] != int(INVALID)
+
+    # ---- access, include/dictionary.hpp:71 ----------------------------------------------------
+    def access_batch(self, kmer_ids, stream: int = 0):
+        kmer_ids = self._prep_in(kmer_ids)
+        n = kmer_ids.numel() if _is_torch(kmer_ids) else kmer_ids.size
+        shape = (n,) if self.words == 1 else (n, 2)
+        out = self._alloc_like(kmer_ids, n, np.uint64, shape)
+        check(self._lib.sshash_gpu_access_batch(self._h, _ptr(kmer_ids), n, _ptr(out), stream))
+        return out
+
+    def access(self, kmer_id: int) -> str:
+        w = self.access_batch(np.array([kmer_id], dtype=np.uint64)).reshape(-1)
+        x = int(w[0]) | (int(w[1]) << 64 if self.words == 2 else 0)
+        return uint_kmer_to_string(x, self.k())
+
+    # ---- streaming, include/streaming_query.hpp + src/query.cpp -------------------------------
+    def streaming_batch(self, bases, read_offsets, want_ids: bool = True, stream: int = 0):
+        """Streaming membership over a batch of reads (concatenated characters + offsets).
+        Returns (kmer_ids or None, report dict)."""
+        if isinstance(bases, (bytes, bytearray)):
+            bases = np.frombuffer(bases, dtype=np.uint8)
+        bases = self._prep_in(bases, np.uint8)
+        read_offsets = self._prep_in(read_offsets)
+        nreads = (read_offsets.numel() if _is_torch(read_offsets) else read_offsets.size) - 1
+        ids = None
+        if want_ids:
+            if _is_torch(read_offsets):
+                lens = read_offsets[1:] - read_offsets[:-1]
+                nwin = int((lens - self.k() + 1).clamp(min=0).sum().item())
+            else:
+                lens = np.diff(read_offsets.astype(np.int64))
+                nwin = int(np.maximum(lens - self.k() + 1, 0).sum())
+            ids = self._alloc_like(read_offsets, max(nwin, 1), np.uint64)[:nwin]
+        rep = StreamingReport()
+        check(self._lib.sshash_gpu_streaming_batch(self._h, _ptr(bases), _ptr(read_offsets), max(nreads, 0),
+                                                   _ptr(ids) if want_ids else None, C.byref(rep), stream))
+        return ids, rep.as_dict()
+
+    def streaming_query_from_file(self, filename: str, multiline: bool = False) -> dict:
+        rep = StreamingReport()
+        check(self._lib.sshash_gpu_streaming_query_from_file(self._h, filename.encode(), int(multiline), C.byref(rep)))
+        return rep.as_dict()
+
+
+def launch_count() -> int:
+    return int(_lib.lib().sshash_gpu_launch_count())

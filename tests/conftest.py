@@ -1,0 +1,53 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_manifest():
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        return json.load(f)
+
+
+MANIFEST = load_manifest()
+FIXTURES = sorted(MANIFEST)
+
+
+@pytest.fixture(scope="session")
+def manifest():
+    return MANIFEST
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.meta = MANIFEST[name]
+        self.index = os.path.join(GOLDEN, name + ".sshash")
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.z = {k: z[k] for k in z.files}
+        self.max_k = self.meta["max_k"]
+        self.words = 1 if self.max_k == 31 else 2
+
+
+_cache = {}
+
+
+def golden(name):
+    if name not in _cache:
+        _cache[name] = Golden(name)
+    return _cache[name]
+
+
+REPORT_KEYS = ("num_kmers", "num_positive_kmers", "num_negative_kmers", "num_invalid_kmers", "num_searches",
+               "num_extensions")

@@ -1,0 +1,61 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/sshash_gpu.h
+declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, golden
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "sshash_gpu.h")).read()
+    return sorted(set(re.findall(r"SSHASH_GPU_API[^;(]*?\b(sshash_gpu_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sshash_b200 import _lib
+    lib = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(syms) == set(_lib.SYMBOLS), "python binding and header disagree"
+    assert b"sm_100a" in lib.sshash_gpu_build_info()
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    from sshash_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_open_errors_without_cpu_fallback(tmp_path):
+    import torch
+    import sshash_b200
+    with pytest.raises(sshash_b200.SshashGpuError, match="EIO"):
+        sshash_b200.Dictionary(str(tmp_path / "missing.sshash"))
+    bad = tmp_path / "bad.sshash"
+    bad.write_bytes(b"\x04\x01\x01" + b"\0" * 100)
+    with pytest.raises(sshash_b200.SshashGpuError, match="MAJOR index version mismatch"):
+        sshash_b200.Dictionary(str(bad))
+    good = open(golden("se_k47_m8").index, "rb").read()
+    bad.write_bytes(good[: len(good) // 3])
+    with pytest.raises(sshash_b200.SshashGpuError, match="EFORMAT"):
+        sshash_b200.Dictionary(str(bad))
+    with pytest.raises(sshash_b200.SshashGpuError, match="EINVAL"):
+        sshash_b200.Dictionary(golden("se_k63_m21").index, max_k=31)
+    if not torch.cuda.is_available():
+        # the product path must refuse to run without a GPU rather than fall back to a CPU path
+        with pytest.raises(sshash_b200.SshashGpuError, match="no CUDA device"):
+            sshash_b200.Dictionary(golden("se_k31_m13").index)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sshash_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "_lib.py" and False, os.path.join(dirpath, f)

@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden vectors and
+the C oracle.  Bit-exact: ids, complete lookup_result records, streaming ids and report counters."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, REPORT_KEYS, golden
+
+pytestmark = pytest.mark.gpu
+
+INVALID = np.uint64(2**64 - 1)
+
+
+@pytest.fixture(scope="module")
+def dicts():
+    import sshash_b200
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            g = golden(name)
+            cache[name] = sshash_b200.Dictionary(g.index, device=0, max_k=g.max_k)
+        return cache[name]
+
+    yield get
+    for d in cache.values():
+        d.close()
+
+
+def test_native_library_loaded_and_counts_launches(dicts):
+    import sshash_b200
+    d = dicts("se_k31_m13")
+    before = sshash_b200.launch_count()
+    d.lookup_batch(np.array([0x1DDB9E97AA56E2D4], dtype=np.uint64))
+    assert sshash_b200.launch_count() == before + 1
+    assert d.info["device_bytes"] > 0 and d.info["num_kmers"] == 4787534
+
+
+def test_known_answer_vectors(dicts):
+    d = dicts("se_k31_m13")
+    assert (d.k(), d.m(), d.canonical(), d.num_kmers(), d.num_strings()) == (31, 13, False, 4787534, 647)
+    r = d.lookup("ACCGTATGTCCCTTTTGCCTTGCTGTCGCGC")
+    assert (r["kmer_id"], r["kmer_orientation"], r["string_id"], r["string_end"]) == (0, 1, 0, 118)
+    r = d.lookup("GCGCGACAGCAAGGCAAAAGGGACATACGGT")
+    assert (r["kmer_id"], r["kmer_orientation"]) == (0, -1)
+    assert d.lookup("GCGCGACAGCAAGGCAAAAGGGACATACGGT", check_reverse_complement=False)["kmer_id"] == int(INVALID)
+    assert d.lookup("CGTCATCAGCATCGGAGGCATCCACCCACGC")["kmer_id"] == 4787533
+    assert d.lookup("cgtcatcagcatcggaggcatccacccacgc")["kmer_id"] == 4787533
+    assert not d.is_member("ACGTACGTACGTACGTACGTACGTACGTACG")
+    assert d.is_member("TCGGCCACGTTGCTGATCGCCCATACCCATT")
+    assert d.access(88) == "GCACTACCAGGAACAACTGGAGCAGCTTAAA"
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_lookup_ids_and_full_records(dicts, name):
+    g, d = golden(name), dicts(name)
+    q = g.z["queries"]
+    ids = d.lookup_batch(q)
+    assert ids.dtype == np.uint64 and (ids == g.z["ids"]).all()
+    assert (d.lookup_batch(q, check_reverse_complement=False) == g.z["ids_norc"]).all()
+    full = d.lookup_batch(q, full=True)
+    for f in full.dtype.names:
+        assert (full[f] == g.z["full"][f]).all(), f
+    assert (d.is_member_batch(q) == (g.z["ids"] != INVALID)).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_lookup_device_buffers(dicts, name):
+    import torch
+    g, d = golden(name), dicts(name)
+    q = torch.from_numpy(g.z["queries"].view(np.int64)).cuda()
+    ids = d.lookup_batch(q)
+    torch.cuda.synchronize()
+    assert ids.is_cuda and (ids.cpu().numpy().view(np.uint64) == g.z["ids"]).all()
+    full = d.lookup_batch(q, full=True)
+    torch.cuda.synchronize()
+    full = full.cpu().numpy()
+    for j, f in enumerate(g.z["full"].dtype.names):
+        assert (full[:, j].view(g.z["full"][f].dtype) == g.z["full"][f]).all(), f
+    mem = d.is_member_batch(q)
+    torch.cuda.synchronize()
+    assert (mem.cpu().numpy().astype(bool) == (g.z["ids"] != INVALID)).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_lookup_ascii(dicts, name):
+    g, d = golden(name), dicts(name)
+    k, w = d.k(), g.words
+    q = g.z["queries"].reshape(-1, w)[:3000]
+    strs = []
+    for row in q:
+        x = int(row[0]) | ((int(row[1]) << 64) if w == 2 else 0)
+        strs.append("".join("ACTG"[(x >> (2 * i)) & 3] for i in range(k)))
+    # packed queries may carry bits above 2k (random negatives are masked in make_golden, so they do not)
+    ids = d.lookup_batch_ascii("".join(strs).encode())
+    assert (ids == g.z["ids"][:3000]).all()
+    ids = d.lookup_batch_ascii("".join(strs).lower().encode())
+    assert (ids == g.z["ids"][:3000]).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_access_and_roundtrip(dicts, name):
+    """test/check.hpp:29-49: lookup(access(id)).kmer_id == id."""
+    g, d = golden(name), dicts(name)
+    npos = g.z["positive_ids"].size
+    rng = np.random.default_rng(3)
+    ids = rng.integers(0, d.num_kmers(), 200000).astype(np.uint64)
+    ids[:4] = [0, 1, d.num_kmers() - 1, d.num_kmers() - 2]
+    kmers = d.access_batch(ids)
+    got = d.lookup_batch(kmers.reshape(-1))
+    assert (got == ids).all()
+    # access agrees with the reference on the golden positives (even positions are forward)
+    acc = d.access_batch(g.z["positive_ids"]).reshape(npos, -1)
+    assert (acc[0::2].reshape(-1) == g.z["queries"].reshape(-1, g.words)[:npos][0::2].reshape(-1)).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_streaming_ids_and_report(dicts, name):
+    g, d = golden(name), dicts(name)
+    ids, rep = d.streaming_batch(g.z["read_bases"], g.z["read_offsets"])
+    assert (ids == g.z["stream_ids"]).all()
+    assert [rep[k] for k in REPORT_KEYS] == g.z["stream_report"].tolist()
+    _, rep2 = d.streaming_batch(g.z["read_bases"], g.z["read_offsets"], want_ids=False)
+    assert rep2 == rep
+
+
+@pytest.mark.parametrize("name", ["se_k31_m13", "se_k63_m8_canon"])
+def test_streaming_device_buffers_and_file(dicts, name, tmp_path):
+    import torch
+    g, d = golden(name), dicts(name)
+    bases = torch.from_numpy(g.z["read_bases"]).cuda()
+    offs = torch.from_numpy(g.z["read_offsets"].view(np.int64)).cuda()
+    ids, rep = d.streaming_batch(bases, offs)
+    torch.cuda.synchronize()
+    assert (ids.cpu().numpy().view(np.uint64) == g.z["stream_ids"]).all()
+    assert [rep[k] for k in REPORT_KEYS] == g.z["stream_report"].tolist()
+    # FASTQ / FASTA files through the host driver (src/query.cpp:53-108)
+    raw = g.z["read_bases"].tobytes().decode()
+    o = g.z["read_offsets"].astype(np.int64)
+    reads = [raw[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+    fq = tmp_path / "reads.fastq"
+    fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(reads)))
+    assert [d.streaming_query_from_file(str(fq))[k] for k in REPORT_KEYS] == g.z["stream_report"].tolist()
+    import gzip
+    fa = tmp_path / "reads.fa.gz"
+    with gzip.open(fa, "wt") as f:
+        f.write("".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(reads)))
+    assert [d.streaming_query_from_file(str(fa))[k] for k in REPORT_KEYS] == g.z["stream_report"].tolist()
+    assert d.streaming_query_from_file(str(tmp_path / "x.txt"))["num_kmers"] == 0  # unsupported extension
+
+
+def test_edge_cases(dicts):
+    d = dicts("se_k31_m13")
+    assert d.lookup_batch(np.zeros(0, dtype=np.uint64)).size == 0
+    ids, rep = d.streaming_batch(b"", np.zeros(1, dtype=np.uint64))
+    assert ids.size == 0 and rep["num_kmers"] == 0
+    # ragged reads: empty, shorter than k, exactly k, all-N
+    reads = ["", "ACGT", "ACCGTATGTCCCTTTTGCCTTGCTGTCGCGC", "N" * 40, "ACCGTATGTCCCTTTTGCCTTGCTGTCGCGCN"]
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    ids, rep = d.streaming_batch("".join(reads).encode(), offs)
+    assert ids.tolist() == [0] + [int(INVALID)] * 10 + [0, int(INVALID)]
+    assert (rep["num_kmers"], rep["num_positive_kmers"], rep["num_invalid_kmers"], rep["num_searches"]) == (13, 2, 11, 2)
+
+
+def test_large_batch_properties():
+    """BASELINE cfg-2 shape at reduced count (1e7): every positive returns its own id, through the
+    chunked host pipeline and through device buffers; 50% reverse-complemented."""
+    import torch
+    import sshash_b200
+    g = golden("se_k31_m13")
+    d = sshash_b200.Dictionary(g.index)
+    n = 10_000_000
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    ids = torch.randint(0, d.num_kmers(), (n,), generator=gen, device="cuda", dtype=torch.int64)
+    kmers = d.access_batch(ids)
+    got = d.lookup_batch(kmers)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ids)
+    host = kmers.cpu().numpy().view(np.uint64)
+    got_h = d.lookup_batch(host)
+    assert (got_h.view(np.int64) == ids.cpu().numpy()).all()
+    neg = torch.randint(0, 2**62, (n,), generator=gen, device="cuda", dtype=torch.int64)
+    got = d.lookup_batch(neg)
+    torch.cuda.synchronize()
+    assert int((got != -1).sum()) == 0
+    d.close()
+
+
+def test_multi_partition_index_vs_oracle(tmp_path):
+    """> 3e6 minimizers => several PTHash partitions; index built on the box by the reference
+    builder (oracle/_ref), CUDA path compared with the C oracle."""
+    from oracle import port, ref
+    if not ref.available(31):
+        pytest.skip("oracle/_ref not built")
+    import sshash_b200
+    rng = np.random.default_rng(11)
+    fa = tmp_path / "synth.fa"
+    with open(fa, "w") as f:
+        for i in range(13000):
+            f.write(">%d\n%s\n" % (i, "".join("ACGT"[c] for c in rng.integers(0, 4, 3000))))
+    idx = str(tmp_path / "synth.sshash")
+    ref.build(str(fa), 31, 14, idx, threads=min(16, os.cpu_count() or 1), tmp_dir=str(tmp_path))
+    o = port.OracleDictionary(idx)
+    d = sshash_b200.Dictionary(idx)
+    assert d.info["mphf_partitions"] >= 2
+    ids = rng.integers(0, o.num_kmers, 100000).astype(np.uint64)
+    pos = d.access_batch(ids)
+    assert (pos == o.access(ids)).all()
+    q = np.concatenate([pos, rng.integers(0, 2**62, 100000).astype(np.uint64)])
+    a, fa_ = o.lookup(q, full=True)
+    full = d.lookup_batch(q, full=True)
+    assert (full["kmer_id"][:100000] == ids).all()
+    for f in full.dtype.names:
+        assert (full[f] == fa_[f]).all(), f
+    d.close()
