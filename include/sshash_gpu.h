@@ -14,9 +14,9 @@
  *     dictionary's GPU; the library detects which (cudaPointerGetAttributes).  Host buffers are
  *     streamed through the GPU in chunks with copies overlapped with the kernels; device buffers
  *     are used in place;
- *   - `stream` is a cudaStream_t passed as void* (NULL = the dictionary's own stream).  With
- *     device buffers the call is asynchronous on that stream; with host buffers it returns when
- *     the outputs are complete;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  With device
+ *     buffers the call is asynchronous on that stream; with host buffers `stream` is ignored, the
+ *     library pipelines the batch on its own streams and returns when the outputs are complete;
  *   - packed k-mers: 2 bits per base, base i at bits [2i, 2i+1], A=0 C=1 T=2 G=3
  *     (include/kmer.hpp:194); one little-endian uint64 per k-mer when the dictionary was opened
  *     with max_k = 31, two (low word first) when max_k = 63 (include/kmer.hpp:304-308);

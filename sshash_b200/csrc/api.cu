@@ -161,7 +161,7 @@ struct Uploader {
 uint64_t shift_mix(uint64_t v) { return v ^ (v >> 47); }
 
 int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
-    Uploader up{d};
+    Uploader up{d, 0, {}};
     DeviceIndex& ix = d->ix;
     ix.k = f.k; ix.m = f.m; ix.canonical = f.canonical ? 1 : 0;
     ix.kmer_words = max_k == 31 ? 1 : 2;
@@ -290,7 +290,7 @@ int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void
     if (n == 0) return SSHASH_GPU_OK;
     const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
     if (in_dev && out_dev) {
-        cudaStream_t s = user_stream ? static_cast<cudaStream_t>(user_stream) : d->stream;
+        cudaStream_t s = static_cast<cudaStream_t>(user_stream);   // NULL = the legacy default stream
         CU(launch(in, out, n, s));
         return SSHASH_GPU_OK;
     }
@@ -390,7 +390,7 @@ static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool 
         if (is_device_pointer(queries) != is_device_pointer(kmer_ids) || is_device_pointer(queries) != is_device_pointer(full))
             return fail(SSHASH_GPU_EINVAL, "kmers, kmer_ids and full must all be host or all be device pointers");
         if (is_device_pointer(queries)) {
-            cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dict->stream;
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
             CU(launch_lookup(ix, sms, queries, ascii, n, rc, kmer_ids, full, nullptr, s));
             return SSHASH_GPU_OK;
         }
@@ -490,7 +490,8 @@ int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, c
         CU(cudaMalloc(reinterpret_cast<void**>(&w.d_counters), 8 * sizeof(unsigned long long)));
         CU(cudaMallocHost(reinterpret_cast<void**>(&w.h_counters), 8 * sizeof(unsigned long long)));
     }
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : dict->stream;
+    // device buffers: the caller's stream (NULL = legacy default stream); host buffers: our own
+    cudaStream_t s = dev ? static_cast<cudaStream_t>(stream) : dict->stream;
     CU(cudaMemsetAsync(w.d_counters, 0, 8 * sizeof(unsigned long long), s));
     if (dev) {
         // total bases bound the number of windows; two 8-byte reads tell us how many

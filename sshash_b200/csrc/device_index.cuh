@@ -174,32 +174,59 @@ struct Minimizer { uint64_t value; uint32_t pos; };
 
 #define SSHASH_MIX_C 0x517cc1b727220a95ull
 
+// Only the running minimum hash and its position are tracked inside the loop; the minimizer value
+// is re-extracted from the k-mer afterwards (two selects fewer per m-mer).  When m <= 16 the m-mer
+// fits 32 bits and the 64-bit multiply by the mixer constant needs two IMADs instead of four.
+// If no hash is < UINT64_MAX the reference leaves minimizer = all ones, pos = 0 (util.hpp:268-270).
+template <bool SMALL_M>
 __device__ __forceinline__ Minimizer compute_minimizer(Kmer<1> x, uint32_t k, uint32_t m, uint64_t magic) {
-    const uint64_t mm = low_mask(2 * m);
-    uint64_t min_hash = ~0ull, mini = ~0ull, v = x.lo;
+    uint64_t min_hash = ~0ull, v = x.lo;
     uint32_t pos = 0;
     const uint32_t n = k - m + 1;
-    for (uint32_t i = 0; i < n; ++i) {
-        uint64_t mmer = v & mm;
-        uint64_t h = (mmer * SSHASH_MIX_C) ^ magic;
-        if (h < min_hash) { min_hash = h; mini = mmer; pos = i; }
-        v >>= 2;
+    if (SMALL_M) {
+        const uint32_t mm = (uint32_t)low_mask(2 * m);
+#pragma unroll 4
+        for (uint32_t i = 0; i < n; ++i) {
+            uint64_t h = ((uint64_t)((uint32_t)v & mm) * SSHASH_MIX_C) ^ magic;
+            if (h < min_hash) { min_hash = h; pos = i; }
+            v >>= 2;
+        }
+    } else {
+        const uint64_t mm = low_mask(2 * m);
+#pragma unroll 4
+        for (uint32_t i = 0; i < n; ++i) {
+            uint64_t h = ((v & mm) * SSHASH_MIX_C) ^ magic;
+            if (h < min_hash) { min_hash = h; pos = i; }
+            v >>= 2;
+        }
     }
+    uint64_t mini = (x.lo >> (2 * pos)) & low_mask(2 * m);
+    if (min_hash == ~0ull) mini = ~0ull;
     return {mini, pos};
 }
+template <bool SMALL_M>
 __device__ __forceinline__ Minimizer compute_minimizer(Kmer<2> x, uint32_t k, uint32_t m, uint64_t magic) {
-    const uint64_t mm = low_mask(2 * m);
-    uint64_t min_hash = ~0ull, mini = ~0ull, lo = x.lo, hi = x.hi;
+    uint64_t min_hash = ~0ull, lo = x.lo, hi = x.hi;
     uint32_t pos = 0;
     const uint32_t n = k - m + 1;
+    const uint64_t mm = low_mask(2 * m);
+#pragma unroll 4
     for (uint32_t i = 0; i < n; ++i) {
-        uint64_t mmer = lo & mm;
-        uint64_t h = (mmer * SSHASH_MIX_C) ^ magic;
-        if (h < min_hash) { min_hash = h; mini = mmer; pos = i; }
+        uint64_t h = SMALL_M ? (((uint64_t)((uint32_t)lo & (uint32_t)mm) * SSHASH_MIX_C) ^ magic)
+                             : (((lo & mm) * SSHASH_MIX_C) ^ magic);
+        if (h < min_hash) { min_hash = h; pos = i; }
         lo = (lo >> 2) | (hi << 62);
         hi >>= 2;
     }
+    const uint32_t s = 2 * pos;   // < 128
+    uint64_t w = s == 0 ? x.lo : (s < 64 ? ((x.lo >> s) | (x.hi << (64 - s))) : (x.hi >> (s - 64)));
+    uint64_t mini = w & mm;
+    if (min_hash == ~0ull) mini = ~0ull;
     return {mini, pos};
+}
+template <int W>
+__device__ __forceinline__ Minimizer compute_minimizer(Kmer<W> x, uint32_t k, uint32_t m, uint64_t magic) {
+    return m <= 16 ? compute_minimizer<true>(x, k, m, magic) : compute_minimizer<false>(x, k, m, magic);
 }
 
 // ------------------------------------------------------------------------------------------------

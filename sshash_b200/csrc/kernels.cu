@@ -62,23 +62,87 @@ __device__ __forceinline__ Kmer<2> pack_ascii<2>(const char* __restrict__ s, uin
 
 // ------------------------------------------------------------------------------------------------
 // batched dictionary::lookup.  MODE 0: ids, 1: ids + full records, 2: membership bytes
+//
+// One thread per query.  On a regular (non-canonical) index a k-mer stored in the other
+// orientation misses the forward pass and needs a second pass on its reverse complement
+// (src/dictionary.cpp:71-76) -- with the reference's 50 % RC query mix that is every other lane,
+// and running the second pass under divergence would idle half of each warp.  Instead each warp
+// parks its missed queries in a small shared-memory queue and runs the reverse-complement pass
+// only on FULL groups of 32 (plus one drain at the end), so both passes execute with all lanes on.
 // ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void emit(uint64_t i, const LookupResult& r, uint64_t* __restrict__ ids,
+                                     sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
+    if (MODE == 2) member[i] = r.kmer_id != ~0ull;
+    else {
+        if (ids) __stcs(ids + i, r.kmer_id);
+        if (MODE == 1) store_full(full, i, r);
+    }
+}
+
+template <int W> struct RcQueue;
+template <> struct RcQueue<1> {
+    uint64_t kmer[64]; uint64_t idx[64];
+    __device__ void put(uint32_t s, Kmer<1> x, uint64_t i) { kmer[s] = x.lo; idx[s] = i; }
+    __device__ Kmer<1> get(uint32_t s) const { return {kmer[s]}; }
+};
+template <> struct RcQueue<2> {
+    uint64_t lo[64]; uint64_t hi[64]; uint64_t idx[64];
+    __device__ void put(uint32_t s, Kmer<2> x, uint64_t i) { lo[s] = x.lo; hi[s] = x.hi; idx[s] = i; }
+    __device__ Kmer<2> get(uint32_t s) const { return {lo[s], hi[s]}; }
+};
+
 template <int W, int MODE, bool ASCII>
 __global__ void __launch_bounds__(kBlock)
 lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
               uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
+    constexpr bool FULL = MODE == 1;
+    __shared__ RcQueue<W> queues[kBlock / 32];
+    RcQueue<W>& q = queues[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t k = ix.k;
+    const bool two_pass = !ix.canonical && check_rc != 0;
+    uint32_t queued = 0;                                  // warp-uniform
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Kmer<W> x;
-        if (ASCII) x = pack_ascii<W>(static_cast<const char*>(queries) + i * ix.k, ix.k);
-        else x = load_kmer<W>(static_cast<const uint64_t*>(queries), i);
-        LookupResult r;
-        lookup_kmer<W, MODE == 1>(ix, x, check_rc != 0, r);
-        if (MODE == 2) member[i] = r.kmer_id != ~0ull;
-        else {
-            if (ids) __stcs(ids + i, r.kmer_id);
-            if (MODE == 1) store_full(full, i, r);
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    for (uint64_t tile = first; tile < n; tile += stride) {   // warp-uniform trip count
+        const uint64_t i = tile + lane;
+        bool park = false;
+        Kmer<W> x{};
+        if (i < n) {
+            if (ASCII) x = pack_ascii<W>(static_cast<const char*>(queries) + i * k, k);
+            else x = load_kmer<W>(static_cast<const uint64_t*>(queries), i);
+            LookupResult r;
+            if (!two_pass) {
+                lookup_kmer<W, FULL>(ix, x, false, r);    // canonical, or regular without the RC retry
+                emit<MODE>(i, r, ids, full, member);
+            } else if (lookup_regular<W, FULL>(ix, x, r)) {
+                emit<MODE>(i, r, ids, full, member);
+            } else {
+                park = true;
+            }
         }
+        if (!two_pass) continue;
+        const uint32_t mask = __ballot_sync(0xffffffffu, park);
+        if (park) q.put(queued + __popc(mask & ((1u << lane) - 1)), kmer_rc(x, k), i);
+        queued += __popc(mask);
+        __syncwarp();
+        if (queued >= 32) {
+            queued -= 32;
+            LookupResult r;
+            const uint64_t qi = q.idx[queued + lane];
+            lookup_regular<W, FULL>(ix, q.get(queued + lane), r);
+            r.kmer_orientation = -1;                      // dictionary.cpp:74-75 (also for a miss)
+            emit<MODE>(qi, r, ids, full, member);
+            __syncwarp();
+        }
+    }
+    if (two_pass && lane < queued) {                      // drain
+        LookupResult r;
+        const uint64_t qi = q.idx[lane];
+        lookup_regular<W, FULL>(ix, q.get(lane), r);
+        r.kmer_orientation = -1;
+        emit<MODE>(qi, r, ids, full, member);
     }
 }
 
