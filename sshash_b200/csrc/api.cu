@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -96,7 +97,7 @@ bool is_device_pointer(const void* p) {
 
 struct sshash_gpu_dict {
     int device = 0;
-    int sm_count = 148;
+    LaunchCtx ctx{};
     DeviceIndex ix{};
     sshash_gpu_info_t info{};
     std::vector<void*> allocs;
@@ -178,14 +179,8 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     for (auto* p : phfs) for (auto const& sp : p->parts) { pilot_words += sp.pilots.data.n; ++n_parts; }
     std::vector<DevPhfPart> parts; parts.reserve(n_parts);
     std::vector<uint32_t> free_pool;
-    uint64_t* d_pilots = nullptr;
-    {
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_pilots), pilot_words * 8 + kPadBytes);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pilots)");
-        d->allocs.push_back(d_pilots);
-        up.bytes += pilot_words * 8 + kPadBytes;
-        CU(cudaMemset(reinterpret_cast<uint8_t*>(d_pilots) + pilot_words * 8, 0, kPadBytes));
-    }
+    // host staging of the pilots pool (copied into the hot slab below)
+    std::vector<uint64_t> pilots_host(pilot_words);
     uint64_t word = 0;
     std::vector<uint64_t> first_part;
     for (auto* p : phfs) {
@@ -198,8 +193,7 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
             o.num_keys = sp.num_keys; o.table_size = sp.table_size; o.num_buckets = sp.num_buckets;
             o.pilots_word = word; o.pilot_mask = sp.pilots.mask; o.pilot_width = (uint32_t)sp.pilots.width;
             o.free_off = free_pool.size();
-            if (sp.pilots.data.n)
-                CU(cudaMemcpy(d_pilots + word, f.ptr(sp.pilots.data), sp.pilots.data.bytes(), cudaMemcpyHostToDevice));
+            if (sp.pilots.data.n) std::memcpy(pilots_host.data() + word, f.ptr(sp.pilots.data), sp.pilots.data.bytes());
             word += sp.pilots.data.n;
             const uint64_t n_free = sp.table_size - sp.num_keys;
             if (n_free) {
@@ -211,9 +205,6 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
             parts.push_back(o);
         }
     }
-    ix.pilots = d_pilots;
-    ix.free_slots = static_cast<const uint32_t*>(up.raw(free_pool.data(), free_pool.size() * 4));
-    const DevPhfPart* d_parts = static_cast<const DevPhfPart*>(up.raw(parts.data(), parts.size() * sizeof(DevPhfPart)));
     auto make_phf = [&](const PartitionedPhfView& p, uint64_t first) {
         DevPhf o{};
         const uint64_t k1 = 0xb492b66fbe98f273ull;
@@ -221,7 +212,7 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         o.city_a = shift_mix(p.seed * k1) * k1;     // cityhash.cpp:245
         o.city_cb = (~p.seed) * k1;                 // cityhash.cpp:246
         o.num_partitions = p.parts.size();
-        o.parts = d_parts + first;
+        o.first_part_ = first;
         return o;
     };
     ix.mphf = make_phf(f.minimizers_mphf, first_part[0]);
@@ -257,11 +248,63 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     }
     ix.n_ends = ends.size();
     ends.push_back(~0ull); ends.push_back(~0ull);   // scan sentinels
-    ix.ends = static_cast<const uint64_t*>(up.raw(ends.data(), ends.size() * 8));
-    ix.ends_dir = static_cast<const uint32_t*>(up.raw(dir.data(), dir.size() * 4));
+
+    // HOT SLAB: the arrays every lookup touches (pilots, free slots, partition table, end-points and
+    // their directory) live in ONE allocation so that a single L2 access-policy window can keep
+    // them persistent in L2 while the cold, much larger arrays (codewords, strings) stream through.
+    struct Piece { const void* src; uint64_t bytes; uint64_t off; };
+    Piece pieces[5] = {{pilots_host.data(), pilots_host.size() * 8, 0}, {free_pool.data(), free_pool.size() * 4, 0},
+                       {parts.data(), parts.size() * sizeof(DevPhfPart), 0}, {ends.data(), ends.size() * 8, 0},
+                       {dir.data(), dir.size() * 4, 0}};
+    uint64_t slab_bytes = 0;
+    for (auto& p : pieces) { p.off = slab_bytes; slab_bytes += (p.bytes + kPadBytes + 255) & ~255ull; }
+    uint8_t* slab = nullptr;
+    {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&slab), slab_bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(hot slab)");
+        d->allocs.push_back(slab);
+        up.bytes += slab_bytes;
+        CU(cudaMemset(slab, 0, slab_bytes));
+        for (auto& p : pieces) if (p.bytes) CU(cudaMemcpy(slab + p.off, p.src, p.bytes, cudaMemcpyHostToDevice));
+    }
+    ix.pilots = reinterpret_cast<const uint64_t*>(slab + pieces[0].off);
+    ix.free_slots = reinterpret_cast<const uint32_t*>(slab + pieces[1].off);
+    const DevPhfPart* d_parts = reinterpret_cast<const DevPhfPart*>(slab + pieces[2].off);
+    ix.ends = reinterpret_cast<const uint64_t*>(slab + pieces[3].off);
+    ix.ends_dir = reinterpret_cast<const uint32_t*>(slab + pieces[4].off);
+    ix.mphf.parts = d_parts + ix.mphf.first_part_;
+    for (uint32_t i = 0; i != ix.n_skew; ++i) ix.skew[i].parts = d_parts + ix.skew[i].first_part_;
+    d->ctx.hot_base = slab;
+    d->ctx.hot_bytes = slab_bytes;
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
     d->info.device_bytes = up.bytes;
     return SSHASH_GPU_OK;
+}
+
+// L2 residency of the hot slab: reserve persisting L2 for it and describe the window that every
+// kernel launch carries as a launch attribute (kernels.cu).  SSHASH_GPU_L2_PERSIST=0 disables it;
+// SSHASH_GPU_L2_FETCH={32,64,128} additionally sets the device's L2 fetch granularity hint.
+void configure_l2(sshash_gpu_dict* d) {
+    LaunchCtx& c = d->ctx;
+    const char* e = std::getenv("SSHASH_GPU_L2_PERSIST");
+    const bool want = !(e && e[0] == '0');
+    c.window_bytes = 0;
+    if (want && c.max_window_bytes && c.max_persist_bytes && c.hot_bytes) {
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        const uint64_t need = std::min<uint64_t>(c.hot_bytes, c.max_persist_bytes);
+        if (cur < need && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, need) != cudaSuccess) cudaGetLastError();
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        if (cur) {
+            c.window_bytes = std::min<uint64_t>(c.hot_bytes, c.max_window_bytes);
+            c.hit_ratio = c.window_bytes <= cur ? 1.0f : (float)((double)cur / (double)c.window_bytes);
+        }
+    }
+    if (const char* g = std::getenv("SSHASH_GPU_L2_FETCH")) {
+        size_t v = (size_t)std::atoi(g);
+        if (v == 32 || v == 64 || v == 128)
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v) != cudaSuccess) cudaGetLastError();
+    }
 }
 
 int check_dict(const sshash_gpu_dict* d) {
@@ -346,7 +389,9 @@ int sshash_gpu_open(const char* index_path, int device, int max_k, sshash_gpu_di
     d->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    d->sm_count = prop.multiProcessorCount;
+    d->ctx.sm_count = prop.multiProcessorCount;
+    d->ctx.max_window_bytes = (uint64_t)std::max(prop.accessPolicyMaxWindowSize, 0);
+    d->ctx.max_persist_bytes = (uint64_t)std::max(prop.persistingL2CacheMaxSize, 0);
     CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     sshash_gpu_info_t& in = d->info;
     in.num_kmers = f.num_kmers; in.num_strings = f.num_strings; in.k = f.k; in.m = f.m;
@@ -359,6 +404,7 @@ int sshash_gpu_open(const char* index_path, int device, int max_k, sshash_gpu_di
     in.device = device;
     st = upload_index(d.get(), f, max_k);
     if (st != SSHASH_GPU_OK) return st;
+    configure_l2(d.get());
     CU(cudaDeviceSynchronize());
     *out = d.release();
     return SSHASH_GPU_OK;
@@ -383,7 +429,7 @@ static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool 
     if (!queries || (!kmer_ids && !full)) return fail(SSHASH_GPU_EINVAL, "null argument");
     const uint64_t in_elem = ascii ? dict->ix.k : 8ull * dict->ix.kmer_words;
     const DeviceIndex& ix = dict->ix;
-    const int sms = dict->sm_count;
+    const LaunchCtx& sms = dict->ctx;
     const bool rc = check_rc != 0;
     if (kmer_ids && full) {
         // both outputs: ids are a column of the full records; produce the records, then the ids
@@ -430,7 +476,7 @@ int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const uint64_t* kmer
     if (n == 0) return SSHASH_GPU_OK;
     if (!kmers || !member) return fail(SSHASH_GPU_EINVAL, "null argument");
     const DeviceIndex& ix = dict->ix;
-    const int sms = dict->sm_count;
+    const LaunchCtx& sms = dict->ctx;
     const bool rc = check_reverse_complement != 0;
     return run_batched(dict, kmers, 8ull * ix.kmer_words, member, 1, n, stream,
                        [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
@@ -445,7 +491,7 @@ int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_id
     if (n == 0) return SSHASH_GPU_OK;
     if (!kmer_ids || !kmers_out) return fail(SSHASH_GPU_EINVAL, "null argument");
     const DeviceIndex& ix = dict->ix;
-    const int sms = dict->sm_count;
+    const LaunchCtx& sms = dict->ctx;
     return run_batched(dict, kmer_ids, 8, kmers_out, 8ull * ix.kmer_words, n, stream,
                        [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
                            return launch_access(ix, sms, static_cast<const uint64_t*>(in), cn, static_cast<uint64_t*>(out), s);
@@ -467,7 +513,7 @@ static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const cha
         w.win_cap = bytes;
     }
     CU(launch_window_offsets(ix.k, d_read_offsets, num_reads, w.d_win_offsets, w.d_block_sums, s));
-    CU(launch_streaming(ix, dict->sm_count, d_bases, d_read_offsets, w.d_win_offsets, num_reads, w.d_win_id, w.d_win_aux,
+    CU(launch_streaming(ix, dict->ctx, d_bases, d_read_offsets, w.d_win_offsets, num_reads, w.d_win_id, w.d_win_aux,
                         d_ids_out, w.d_counters, s));
     return SSHASH_GPU_OK;
 }

@@ -53,6 +53,7 @@ struct DevPhf {                // pthash::partitioned_phf, partitioned_phf.hpp:1
     uint64_t city_cb;          // (~seed) * k1                     hoisted to the host
     uint64_t num_partitions;
     const DevPhfPart* parts;
+    uint64_t first_part_;      // host-side scratch while the partition table is being placed
 };
 
 struct DeviceIndex {
@@ -99,6 +100,39 @@ __device__ __forceinline__ uint64_t low_mask(uint32_t bits) {  // bits in [0,64]
     return bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Loads with an L2 eviction policy.  The index arrays fall into two classes:
+//   HOT  (pilots, free slots, end-points + directory: tens of MB, touched by every lookup) are
+//        loaded evict_last so that they stay resident in the 126 MB L2;
+//   COLD (control codewords, strings, bucket arrays: up to GBs, one random sector per lookup)
+//        are loaded evict_first so that they do not push the hot arrays out.
+// createpolicy with constant operands folds into a uniform descriptor register (no per-thread cost).
+// ------------------------------------------------------------------------------------------------
+template <bool HOT>
+__device__ __forceinline__ uint64_t l2_policy() {
+    uint64_t p;
+    if (HOT) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// COLD loads additionally carry .L2::64B: measured on B200 (tools/micro/gather.cu) a default load
+// that misses L2 pulls 128 B from HBM, with .L2::64B it pulls 64 B -- the minimum -- which halves
+// the DRAM traffic of the random codeword / strings accesses.
+template <bool HOT>
+__device__ __forceinline__ uint64_t ld64(const uint64_t* __restrict__ p) {
+    uint64_t v;
+    if (HOT) asm("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<true>()));
+    else asm("ld.global.nc.L2::cache_hint.L2::64B.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<false>()));
+    return v;
+}
+template <bool HOT>
+__device__ __forceinline__ uint32_t ld32(const uint32_t* __restrict__ p) {
+    uint32_t v;
+    if (HOT) asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<true>()));
+    else asm("ld.global.nc.L2::cache_hint.L2::64B.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<false>()));
+    return v;
+}
+
 // dna_uint_kmer_t::crc64, include/kmer.hpp:141-157: complement (xor 0b10 per base), then reverse
 // the order of the 32 two-bit groups.  __brevll reverses single bits, so the two bits inside each
 // group are swapped back afterwards.
@@ -124,9 +158,9 @@ __device__ __forceinline__ uint64_t mmer_rc(uint64_t x, uint32_t m) { return rc6
 __device__ __forceinline__ uint64_t read_word64(const uint64_t* __restrict__ data, uint64_t pos) {
     uint64_t w = pos >> 6;
     uint32_t s = (uint32_t)pos & 63u;
-    uint64_t a = __ldg(data + w);
+    uint64_t a = ld64<false>(data + w);
     if (s == 0) return a;
-    uint64_t b = __ldg(data + w + 1);
+    uint64_t b = ld64<false>(data + w + 1);
     return (a >> s) | (b << (64 - s));
 }
 
@@ -137,11 +171,11 @@ __device__ __forceinline__ Kmer<1> read_kmer(const DeviceIndex& ix, uint64_t bas
 __device__ __forceinline__ Kmer<2> read_kmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t k, Kmer<2>*) {
     uint64_t pos = 2 * base_offset, w = pos >> 6;
     uint32_t s = (uint32_t)pos & 63u;
-    uint64_t a = __ldg(ix.strings + w), b = __ldg(ix.strings + w + 1);
+    uint64_t a = ld64<false>(ix.strings + w), b = ld64<false>(ix.strings + w + 1);
     Kmer<2> r;
     if (s == 0) { r.lo = a; r.hi = b; }
     else {
-        uint64_t c = __ldg(ix.strings + w + 2);
+        uint64_t c = ld64<false>(ix.strings + w + 2);
         r.lo = (a >> s) | (b << (64 - s));
         r.hi = (b >> s) | (c << (64 - s));
     }
@@ -155,15 +189,17 @@ __device__ __forceinline__ uint64_t read_mmer(const DeviceIndex& ix, uint64_t ba
 
 // compact_vector::access, compact_vector.hpp:253-260 (two aligned word loads instead of one
 // unaligned 8-byte load)
+template <bool HOT>
 __device__ __forceinline__ uint64_t compact_get(const uint64_t* __restrict__ data, uint32_t width, uint64_t mask, uint64_t i) {
     uint64_t pos = i * width, w = pos >> 6;
     uint32_t s = (uint32_t)pos & 63u;
-    uint64_t v = __ldg(data + w) >> s;
-    if (s + width > 64) v |= __ldg(data + w + 1) << (64 - s);
+    uint64_t v = ld64<HOT>(data + w) >> s;
+    if (s + width > 64) v |= ld64<HOT>(data + w + 1) << (64 - s);
     return v & mask;
 }
+template <bool HOT>
 __device__ __forceinline__ uint64_t compact_get(const DevCompact& c, uint64_t i) {
-    return compact_get(c.data, c.width, c.mask, i);
+    return compact_get<HOT>(c.data, c.width, c.mask, i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -270,9 +306,9 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
     const uint64_t h1 = h.first;
     uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
     uint64_t bucket = __umul64hi(H, p->num_buckets);
-    uint64_t pilot = compact_get(ix.pilots + p->pilots_word, p->pilot_width, p->pilot_mask, bucket);
+    uint64_t pilot = compact_get<true>(ix.pilots + p->pilots_word, p->pilot_width, p->pilot_mask, bucket);
     uint64_t pos = __umul64hi((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, p->table_size);
-    if (pos >= p->num_keys) pos = __ldg(ix.free_slots + p->free_off + (pos - p->num_keys));
+    if (pos >= p->num_keys) pos = ld32<true>(ix.free_slots + p->free_off + (pos - p->num_keys));
     return p->offset + pos;
 }
 
@@ -283,10 +319,10 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_t x, uint64_t& begin, uint64_t& end) {
     // ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none): ends[i] <= x holds
-    uint64_t i = __ldg(ix.ends_dir + (x >> ix.dir_shift));
-    uint64_t cur = __ldg(ix.ends + i), next = __ldg(ix.ends + i + 1);
+    uint64_t i = ld32<true>(ix.ends_dir + (x >> ix.dir_shift));
+    uint64_t cur = ld64<true>(ix.ends + i), next = ld64<true>(ix.ends + i + 1);
     // advance to the last end-point <= x; at most (1 << dir_shift) / k + 1 steps
-    while (next <= x) { cur = next; ++i; next = __ldg(ix.ends + i + 1); }
+    while (next <= x) { cur = next; ++i; next = ld64<true>(ix.ends + i + 1); }
     begin = cur; end = next;
     return i;
 }
@@ -318,7 +354,7 @@ template <int W>
 __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t minimizer, Kmer<W> skew_key,
                                               uint64_t& first, bool& heavy) {
     uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
-    uint64_t code = compact_get(ix.codewords, id);
+    uint64_t code = compact_get<false>(ix.codewords, id);
     heavy = false;
     if ((code & 1) == 0) { first = code >> 1; return 1; }                         // SINGLETON
     if ((code & 3) == 1) {                                                        // MIDLOAD
@@ -332,13 +368,13 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
     uint32_t part = (uint32_t)code & 7;
     uint64_t begin = code >> 3;
     uint64_t kid = phf_position(ix, ix.skew[part], skew_hash(ix.skew[part], skew_key));
-    uint64_t pos_in_bucket = compact_get(ix.skew_pos[part], kid);
+    uint64_t pos_in_bucket = compact_get<false>(ix.skew_pos[part], kid);
     uint64_t idx = begin + pos_in_bucket;
     // A k-mer that was never a key gets an arbitrary slot; the reference then reads past the bucket
     // (spss.hpp:51-63).  Whatever is read cannot make the k-mer comparison succeed for an absent
     // k-mer, so clamping yields the same answer without the out-of-bounds access.
     if (idx >= ix.heavy.size) idx = ix.heavy.size - 1;
-    first = compact_get(ix.heavy, idx);
+    first = compact_get<false>(ix.heavy, idx);
     heavy = true;
     return 1;
 }
@@ -354,12 +390,12 @@ __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x,
     Minimizer mi = compute_minimizer(x, k, m, ix.magic);
     uint64_t first; bool heavy;
     uint32_t n = bucket_of<W>(ix, mi.value, x, first, heavy);
-    uint64_t off0 = (n == 1) ? first : compact_get(ix.mid_load, first);
+    uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {
         if (read_mmer(ix, off0, m) != mi.value) { result_clear(res, heavy); return false; }
     }
     for (uint32_t i = 0; i < n; ++i) {
-        uint64_t off = (i == 0) ? off0 : compact_get(ix.mid_load, first + i);
+        uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
         if (off < mi.pos) continue;
         uint64_t ko = off - mi.pos;
         if (!kmer_eq(read_kmer(ix, ko, k, (Kmer<W>*)nullptr), x)) continue;
@@ -388,13 +424,13 @@ __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kme
     Kmer<W> canon = kmer_lt(x, xr) ? x : xr;            // std::min(uint_kmer, uint_kmer_rc), dictionary.cpp:53
     uint64_t first; bool heavy;
     uint32_t n = bucket_of<W>(ix, mi.value, canon, first, heavy);
-    uint64_t off0 = (n == 1) ? first : compact_get(ix.mid_load, first);
+    uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {
         uint64_t rm = read_mmer(ix, off0, m);
         if (rm != mi.value && rm != mmer_rc(mi.value, m)) { result_clear(res, heavy); return false; }
     }
     for (uint32_t i = 0; i < n; ++i) {
-        uint64_t off = (i == 0) ? off0 : compact_get(ix.mid_load, first + i);
+        uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             uint32_t p = t == 0 ? mi.pos : k - m - mi.pos;

@@ -9,11 +9,16 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 namespace sshash_b200 {
 
 namespace {
 
 constexpr int kBlock = 256;
+// 6 resident CTAs/SM (<= 40 registers, 75 % occupancy): measured best on B200 for both the L2-resident
+// and the HBM-resident case (sweep over 3/4/5/6/8 in profiles/r1_notes.md)
+constexpr int kLookupMinBlocks = 6;
 
 template <int W>
 __device__ __forceinline__ Kmer<W> load_kmer(const uint64_t* __restrict__ kmers, uint64_t i);
@@ -92,8 +97,8 @@ template <> struct RcQueue<2> {
     __device__ Kmer<2> get(uint32_t s) const { return {lo[s], hi[s]}; }
 };
 
-template <int W, int MODE, bool ASCII>
-__global__ void __launch_bounds__(kBlock)
+template <int W, int MODE, bool ASCII, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
               uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
     constexpr bool FULL = MODE == 1;
@@ -162,7 +167,7 @@ access_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict
         uint64_t lo = 0, hi = ix.n_ends - 1;
         while (hi - lo > 1) {
             uint64_t mid = lo + (hi - lo) / 2;
-            if (__ldg(ix.ends + mid) - mid * km1 <= id) lo = mid; else hi = mid;
+            if (ld64<true>(ix.ends + mid) - mid * km1 <= id) lo = mid; else hi = mid;
         }
         store_kmer(kmers_out, i, read_kmer(ix, id + lo * km1, ix.k, (Kmer<W>*)nullptr));
     }
@@ -317,7 +322,7 @@ stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restric
                     n_search += 1;
                     backward = (aux >> 63) != 0;
                     const uint64_t sid = aux & ((1ull << 62) - 1);
-                    const uint64_t sb = __ldg(ix.ends + sid), se = __ldg(ix.ends + sid + 1);
+                    const uint64_t sb = ld64<true>(ix.ends + sid), se = ld64<true>(ix.ends + sid + 1);
                     const uint64_t ko = cur_id + sid * (k - 1);          // kmer_offset in bases
                     const uint64_t in_string = ko - sb;
                     uint64_t bitpos = 2 * ko;
@@ -413,7 +418,33 @@ win_offsets_kernel(uint32_t k, const uint64_t* __restrict__ ro, uint64_t num_rea
     }
 }
 
+
 std::atomic<uint64_t> g_launches{0};
+
+// every kernel of the lookup path is launched through here: <<<grid, kBlock>>> plus the L2
+// access-policy window that keeps the hot slab (pilots, end-points, ...) persistent in L2
+template <typename... KArgs, typename... Args>
+cudaError_t launch(void (*kernel)(KArgs...), int grid, cudaStream_t stream, const LaunchCtx& ctx, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (ctx.window_bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(ctx.hot_base);
+        attr[0].val.accessPolicyWindow.num_bytes = ctx.window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = ctx.hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 1;
+    }
+    g_launches.fetch_add(1);
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 inline int grid_for(uint64_t n, int sm_count, int blocks_per_sm) {
     uint64_t need = (n + kBlock - 1) / kBlock;
@@ -426,14 +457,15 @@ inline int grid_for(uint64_t n, int sm_count, int blocks_per_sm) {
 
 uint64_t kernel_launch_count() { return g_launches.load(); }
 
-cudaError_t launch_lookup(const DeviceIndex& ix, int sm_count, const void* queries, bool ascii, uint64_t n, bool check_rc,
+cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const void* queries, bool ascii, uint64_t n, bool check_rc,
                           uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    const int grid = grid_for(n, sm_count, 8);
+    const int grid = grid_for(n, ctx.sm_count, 2 * kLookupMinBlocks);
     const int mode = member ? 2 : (full ? 1 : 0);
     const int crc = check_rc ? 1 : 0;
+    cudaError_t err = cudaSuccess;
 #define SSHASH_LAUNCH(W, MODE, ASCII) \
-    lookup_kernel<W, MODE, ASCII><<<grid, kBlock, 0, stream>>>(ix, queries, n, crc, ids, full, member)
+    err = launch(lookup_kernel<W, MODE, ASCII, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
 #define SSHASH_DISPATCH_MODE(W, ASCII)                     \
     do {                                                   \
         if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);         \
@@ -444,18 +476,15 @@ cudaError_t launch_lookup(const DeviceIndex& ix, int sm_count, const void* queri
     else { if (ascii) SSHASH_DISPATCH_MODE(2, true); else SSHASH_DISPATCH_MODE(2, false); }
 #undef SSHASH_DISPATCH_MODE
 #undef SSHASH_LAUNCH
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
+    return err;
 }
 
-cudaError_t launch_access(const DeviceIndex& ix, int sm_count, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
+cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
                           cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    const int grid = grid_for(n, sm_count, 8);
-    if (ix.kmer_words == 1) access_kernel<1><<<grid, kBlock, 0, stream>>>(ix, ids, n, kmers_out);
-    else access_kernel<2><<<grid, kBlock, 0, stream>>>(ix, ids, n, kmers_out);
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
+    const int grid = grid_for(n, ctx.sm_count, 8);
+    if (ix.kmer_words == 1) return launch(access_kernel<1>, grid, stream, ctx, ix, ids, n, kmers_out);
+    return launch(access_kernel<2>, grid, stream, ctx, ix, ids, n, kmers_out);
 }
 
 uint64_t window_offsets_scratch_words(uint64_t num_reads) { return (num_reads + 1 + kScanTile - 1) / kScanTile + 1; }
@@ -470,30 +499,26 @@ cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint
     return cudaGetLastError();
 }
 
-cudaError_t launch_streaming(const DeviceIndex& ix, int sm_count, const char* bases, const uint64_t* read_offsets,
+cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
                              const uint64_t* win_offsets, uint64_t num_reads, uint64_t* win_id, uint64_t* win_aux,
                              uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream) {
     if (num_reads == 0) return cudaSuccess;
     {
         uint64_t threads = num_reads * 32;
-        const int grid = grid_for(threads, sm_count, 8);
+        const int grid = grid_for(threads, ctx.sm_count, 8);
+        cudaError_t e;
         if (ix.kmer_words == 1)
-            stream_windows_kernel<1><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
+            e = launch(stream_windows_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
         else
-            stream_windows_kernel<2><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
-        g_launches.fetch_add(1);
-        cudaError_t e = cudaGetLastError();
+            e = launch(stream_windows_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
         if (e != cudaSuccess) return e;
     }
     {
-        const int grid = grid_for(num_reads, sm_count, 8);
+        const int grid = grid_for(num_reads, ctx.sm_count, 8);
         if (ix.kmer_words == 1)
-            stream_scan_kernel<1><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
-        else
-            stream_scan_kernel<2><<<grid, kBlock, 0, stream>>>(ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
-        g_launches.fetch_add(1);
+            return launch(stream_scan_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
+        return launch(stream_scan_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace sshash_b200

@@ -11,15 +11,25 @@
 
 namespace sshash_b200 {
 
+// per-dictionary launch facts: grid sizing and the L2 access-policy window over the hot slab
+struct LaunchCtx {
+    int sm_count = 148;
+    const void* hot_base = nullptr;
+    uint64_t hot_bytes = 0;
+    uint64_t window_bytes = 0;      // 0 = no window
+    float hit_ratio = 1.0f;
+    uint64_t max_window_bytes = 0, max_persist_bytes = 0;
+};
+
 // number of kernels launched by this library since it was loaded (bench.py's `gpu_launches`)
 uint64_t kernel_launch_count();
 
 // Batched dictionary::lookup.  `queries`: packed k-mers (ascii = false) or n*k characters.
 // Exactly one of {ids and/or full, member} is produced; all pointers are DEVICE pointers.
-cudaError_t launch_lookup(const DeviceIndex& ix, int sm_count, const void* queries, bool ascii, uint64_t n, bool check_rc,
+cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const void* queries, bool ascii, uint64_t n, bool check_rc,
                           uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream);
 
-cudaError_t launch_access(const DeviceIndex& ix, int sm_count, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
+cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
                           cudaStream_t stream);
 
 // win_offsets[r] = number of windows in reads [0, r), computed on the device from read_offsets
@@ -29,7 +39,7 @@ uint64_t window_offsets_scratch_words(uint64_t num_reads);
 
 // Streaming membership over a batch of reads: per-window lookups, then the per-read replay of the
 // reference state machine.  counters[5] += {num_kmers, searches, extensions, negative, invalid}.
-cudaError_t launch_streaming(const DeviceIndex& ix, int sm_count, const char* bases, const uint64_t* read_offsets,
+cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
                              const uint64_t* win_offsets, uint64_t num_reads, uint64_t* win_id, uint64_t* win_aux,
                              uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream);
 
