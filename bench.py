@@ -124,6 +124,26 @@ def recorded_traffic():
     return None
 
 
+def scale_workload():
+    """Secondary, HBM-resident workload: a synthetic 5e8-k-mer k=31 m=17 index
+    built on this box by the unmodified reference builder (oracle/_ref; index construction is out of
+    scope), 1e8 positive / negative queries, device-resident.  Reported beside the headline line."""
+    try:
+        import tempfile
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import scale_bench
+        wd = tempfile.mkdtemp(prefix="sshash_scale_")
+        r = scale_bench.run(500000, 1030, 31, 17, False, 100_000_000, wd)
+        peak, _ = measured_peak()
+        for key, b_alg in (("positive_forward", 208.0), ("positive_50rc", 256.0), ("negative", 208.0)):
+            r[key]["roofline_frac"] = b_alg * r[key]["lookups_per_s"] / 1e9 / peak
+            r[key]["algorithmic_bytes_per_lookup"] = b_alg
+        r["workload"] = "T5e8: synthetic 5e5 strings x 1030 bases, k=31 m=17 (5e8 k-mers, HBM-resident), 1e8 queries"
+        return r
+    except Exception as e:  # no reference builder on this box, out of disk, ...
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -195,6 +215,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--queries", type=int, default=QUERIES_PER_GPU, help="queries per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scale", action="store_true", help="skip the HBM-resident 5e8-k-mer secondary workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -284,22 +305,27 @@ def main():
     e2e_value = world * n * args.steps / e2e_s
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- NCCL gather of the ids to rank 0 (the only collective of the sharded design), timed apart --
+    # ---- NCCL gather of the ids to rank 0 (the only collective of the sharded design), timed apart:
+    # sshash_b200.sharded.ShardedLookup = shard lookup + chunked p2p gather overlapped with the kernels
     gather = None
     if world > 1:
-        glist = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        from sshash_b200.sharded import ShardedLookup
+        sl = ShardedLookup.for_dictionary(d, chunk_queries=1 << 24)
         for _ in range(2):
-            dist.gather(out, glist, dst=0)
+            sl.lookup(kmers, dst=0)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.gather(out, glist, dst=0)
+        local_ids, gathered = sl.lookup(kmers, dst=0)
         g1.record()
         barrier()
+        assert torch.equal(local_ids, ids)
+        if rank == 0:
+            assert torch.equal(gathered[:n], ids)
         gt = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
         dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gt.item()), "bytes_to_rank0": (world - 1) * n * 8,
-                  "GBps": (world - 1) * n * 8 / (float(gt.item()) * 1e-3) / 1e9}
+        gather = {"lookup_plus_gather_ms": float(gt.item()), "bytes_to_rank0": (world - 1) * n * 8,
+                  "lookups_per_s_with_gather": world * n / (float(gt.item()) * 1e-3)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -322,6 +348,8 @@ def main():
         }
         if gather:
             line["gather"] = gather
+        if world == 1 and not args.no_scale:
+            line["scale"] = scale_workload()
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             sample = h_in_np[:CPU_SAMPLE]
