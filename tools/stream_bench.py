@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Streaming-membership throughput (BASELINE.json configs[2]): synthetic 150-bp reads, 50 % of the
+reads are substrings of indexed strings (random strand), 50 % i.i.d. ACGT, 1 read in 1000 with an N.
+
+    python tools/stream_bench.py [--index tests/golden/se_k31_m13.sshash] [--reads 1000000]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make_reads(d, n_reads, read_len=150, seed=42, device="cuda"):
+    """Returns (bases uint8 tensor on device, offsets int64 tensor on device)."""
+    import torch
+    k = d.k()
+    nwin = read_len - k + 1
+    gen = torch.Generator(device=device).manual_seed(seed)
+    n_pos = n_reads // 2
+    start = torch.randint(0, d.num_kmers() - nwin, (n_pos,), generator=gen, device=device, dtype=torch.int64)
+    ids = (start[:, None] + torch.arange(nwin, device=device)[None, :]).reshape(-1)
+    km = d.access_batch(ids).reshape(n_pos, nwin, -1)
+    # bases of the first k-mer + last base of every following k-mer
+    codes = torch.empty((n_pos, read_len), dtype=torch.int64, device=device)
+    first = km[:, 0, :]
+    for i in range(k):
+        w = first[:, i // 32]
+        codes[:, i] = (w >> (2 * (i % 32))) & 3
+    lastw = km[:, 1:, (k - 1) // 32]
+    codes[:, k:] = (lastw >> (2 * ((k - 1) % 32))) & 3
+    # random strand: reverse + complement (A0 C1 T2 G3: complement = xor 2)
+    flip = torch.rand(n_pos, generator=gen, device=device) < 0.5
+    rc = (codes.flip(1) ^ 2)
+    codes = torch.where(flip[:, None], rc, codes)
+    lut = torch.tensor(list(b"ACTG"), dtype=torch.uint8, device=device)
+    pos_reads = lut[codes]
+    neg_reads = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)[
+        torch.randint(0, 4, (n_reads - n_pos, read_len), generator=gen, device=device)]
+    reads = torch.empty((n_reads, read_len), dtype=torch.uint8, device=device)
+    reads[0::2] = pos_reads[: (n_reads + 1) // 2]
+    reads[1::2] = neg_reads[: n_reads // 2]
+    nn = torch.arange(0, n_reads, 1000, device=device)
+    reads[nn, torch.randint(0, read_len, (nn.numel(),), generator=gen, device=device)] = ord("N")
+    offsets = torch.arange(0, (n_reads + 1) * read_len, read_len, device=device, dtype=torch.int64)
+    return reads.reshape(-1), offsets
+
+
+def run(index, n_reads, steps=3, max_k=0, check=True):
+    import torch
+    import sshash_b200
+    d = sshash_b200.Dictionary(index, max_k=max_k)
+    bases, offs = make_reads(d, n_reads)
+    k = d.k()
+    nwin = n_reads * (150 - k + 1)
+    res = {"index": os.path.basename(index), "reads": n_reads, "windows": nwin}
+    # device-resident, report only
+    for want_ids in (False, True):
+        d.streaming_batch(bases, offs, want_ids=want_ids)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ids, rep = d.streaming_batch(bases, offs, want_ids=want_ids)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        res["device_ids" if want_ids else "device_report_only"] = {"ms": dt * 1e3, "windows_per_s": nwin / dt}
+    res["report"] = rep
+    # host buffers (pinned), report only = the reference's streaming_query_from_file contract
+    hb = torch.empty(bases.numel(), dtype=torch.uint8, pin_memory=True)
+    hb.copy_(bases)
+    ho = offs.cpu().numpy().view(np.uint64)
+    hbn = hb.numpy()
+    d.streaming_batch(hbn, ho, want_ids=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, rep_h = d.streaming_batch(hbn, ho, want_ids=False)
+    dt = (time.perf_counter() - t0) / steps
+    res["host_report_only"] = {"ms": dt * 1e3, "windows_per_s": nwin / dt}
+    assert rep_h == rep
+    if check:
+        from oracle import port
+        o = port.OracleDictionary(index, max_k=max_k)
+        m = min(n_reads, 20000)
+        t0 = time.perf_counter()
+        oids, _, orep = o.streaming_reads(hbn[: m * 150].tobytes(), ho[: m + 1])
+        res["oracle_cpu_windows_per_s_1thread"] = oids.size / (time.perf_counter() - t0)
+        gids, grep = d.streaming_batch(hbn[: m * 150], ho[: m + 1])
+        assert (gids == oids).all() and grep == orep, "streaming differs from the oracle"
+        res["checked_reads_vs_oracle"] = m
+    d.close()
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--index", default=os.path.join(ROOT, "tests", "golden", "se_k31_m13.sshash"))
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--max-k", type=int, default=0)
+    a = ap.parse_args()
+    print(json.dumps(run(a.index, a.reads, max_k=a.max_k)))
