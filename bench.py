@@ -113,12 +113,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic():
-    """dram bytes per launch of the lookup kernel from the committed ncu capture, if any."""
+def recorded_traffic(n_queries: int):
+    """dram bytes per launch of the lookup kernel, from the committed ncu --set full capture
+    (profiles/traffic.json holds the per-query figure; one launch = n_queries queries)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("cfg2_lookup_kernel_dram_bytes_per_launch")
+            return json.load(open(p))["cfg2_lookup_kernel_dram_bytes_per_query"] * n_queries
         except Exception:
             return None
     return None
@@ -342,7 +343,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(), "peak_source": peak_src,
+                         "traffic": recorded_traffic(n), "peak_source": peak_src,
                          "algorithmic_bytes_per_lookup": B_ALG, "kernel": "lookup_kernel<1,0,false>",
                          "kernel_ms_per_launch": per_launch_ms},
         }
