@@ -385,9 +385,8 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
 // it the k-mer comparison alone decides, which yields the same ids (a k-mer match implies the
 // m-mer match because the minimizer is a substring of the k-mer at pos_in_kmer).
 template <int W, bool FULL>
-__device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
+__device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<W> x, Minimizer mi, LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
-    Minimizer mi = compute_minimizer(x, k, m, ix.magic);
     uint64_t first; bool heavy;
     uint32_t n = bucket_of<W>(ix, mi.value, x, first, heavy);
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
@@ -413,6 +412,11 @@ __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x,
     }
     result_clear(res, true);
     return false;
+}
+
+template <int W, bool FULL>
+__device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
+    return lookup_regular_with<W, FULL>(ix, x, compute_minimizer(x, ix.k, ix.m, ix.magic), res);
 }
 
 // Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)

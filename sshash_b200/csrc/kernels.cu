@@ -174,10 +174,20 @@ access_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// streaming membership, step 1: one independent lookup per window.  The reference defines every
-// streamed result as equal to dict->lookup(kmer) (include/streaming_query.hpp:107), which is what
-// makes the windows independent.  One WARP per read; lanes stride over the read's windows so the
-// character loads of neighbouring windows hit the same L1 lines.
+// streaming membership, step 1: one lookup per window.  The reference defines every streamed
+// result as equal to dict->lookup(kmer) (include/streaming_query.hpp:107), which is what makes the
+// windows independent.  One WARP per read, one lane per window, 32 windows (a "tile") at a time;
+// the work that neighbouring windows share is done once per tile:
+//   * characters: every lane loads ONE character per 32-character block, converts it to 2 bits
+//     (include/kmer.hpp:194) and the warp ORs the shifted codes together with redux.sync: the tile's
+//     2-bit packed text appears in all lanes in 2 instructions per 32 bases; lane j's k-mer is a
+//     funnel shift of it.  Validity (kmer.hpp:209-219) is a ballot of the per-character flags.
+//   * minimizers: the hash of every m-mer position of the tile is computed once (forward and
+//     reverse-complement strand) into shared memory; each window then takes the minimum over its
+//     k-m+1 positions (leftmost for the forward strand, rightmost for the RC strand, which is the
+//     leftmost of the reversed order -- include/util.hpp:262-283 on kmer and on kmer_rc).
+//   * on a regular index, windows that miss the forward pass are parked in a per-warp queue and
+//     their reverse-complement pass runs on full groups of 32 lanes (as in lookup_kernel).
 // Window record: id (u64) + string_id (low 62 bits) | flags (bit 63: backward, bit 62: valid)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool valid_base(uint8_t c) {  // canonicalize_basepair_forward_map, kmer.hpp:209-219
@@ -185,33 +195,172 @@ __device__ __forceinline__ bool valid_base(uint8_t c) {  // canonicalize_basepai
     return u == 'A' || u == 'C' || u == 'G' || u == 'T';
 }
 
+// 32 characters (one per lane) -> 64-bit word of 2-bit codes, replicated in every lane
+__device__ __forceinline__ uint64_t pack_tile_word(uint32_t code, uint32_t lane) {
+    const uint32_t sh = 2 * (lane & 15);
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, lane < 16 ? code << sh : 0u);
+    const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? 0u : code << sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+// bits [2*j, 2*j + 64) of the 192-bit little-endian value (w0, w1, w2); j < 32
+__device__ __forceinline__ uint64_t funnel64(uint64_t w0, uint64_t w1, uint32_t j) {
+    const uint32_t s = 2 * j;
+    return s == 0 ? w0 : (w0 >> s) | (w1 << (64 - s));
+}
+
+constexpr int kTilePositions = 96;   // m-mer start positions covered by one tile: 32 + (k - m) <= 94
+
+template <int W> struct StreamQueue;
+template <> struct StreamQueue<1> {
+    uint64_t kmer[64], mini[64], widx[64]; uint32_t pos[64];
+    __device__ void put(uint32_t s, Kmer<1> x, Minimizer mi, uint64_t w) { kmer[s] = x.lo; mini[s] = mi.value; pos[s] = mi.pos; widx[s] = w; }
+    __device__ Kmer<1> get(uint32_t s) const { return {kmer[s]}; }
+};
+template <> struct StreamQueue<2> {
+    uint64_t lo[64], hi[64], mini[64], widx[64]; uint32_t pos[64];
+    __device__ void put(uint32_t s, Kmer<2> x, Minimizer mi, uint64_t w) { lo[s] = x.lo; hi[s] = x.hi; mini[s] = mi.value; pos[s] = mi.pos; widx[s] = w; }
+    __device__ Kmer<2> get(uint32_t s) const { return {lo[s], hi[s]}; }
+};
+
+__device__ __forceinline__ void store_window(uint64_t* __restrict__ win_id, uint64_t* __restrict__ win_aux, uint64_t w,
+                                             const LookupResult& r, bool backward) {
+    win_id[w] = r.kmer_id;
+    win_aux[w] = (1ull << 62) | (r.string_id & ((1ull << 62) - 1)) | (backward ? (1ull << 63) : 0);
+}
+
 template <int W>
-__global__ void __launch_bounds__(kBlock)
+__device__ __forceinline__ Kmer<W> tile_kmer(uint64_t a, uint64_t b, uint64_t c, uint32_t lane, uint32_t k);
+template <>
+__device__ __forceinline__ Kmer<1> tile_kmer<1>(uint64_t a, uint64_t b, uint64_t, uint32_t lane, uint32_t k) {
+    return {funnel64(a, b, lane) & low_mask(2 * k)};
+}
+template <>
+__device__ __forceinline__ Kmer<2> tile_kmer<2>(uint64_t a, uint64_t b, uint64_t c, uint32_t lane, uint32_t k) {
+    Kmer<2> r{funnel64(a, b, lane), funnel64(b, c, lane)};
+    if (2 * k <= 64) { r.lo &= low_mask(2 * k); r.hi = 0; } else r.hi &= low_mask(2 * k - 64);
+    return r;
+}
+__device__ __forceinline__ uint64_t kmer_bits_at(Kmer<1> x, uint32_t pos, uint32_t m) { return (x.lo >> (2 * pos)) & low_mask(2 * m); }
+__device__ __forceinline__ uint64_t kmer_bits_at(Kmer<2> x, uint32_t pos, uint32_t m) {
+    const uint32_t s = 2 * pos;
+    uint64_t w = s == 0 ? x.lo : (s < 64 ? ((x.lo >> s) | (x.hi << (64 - s))) : (x.hi >> (s - 64)));
+    return w & low_mask(2 * m);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBlock, 4)
 stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
                       const uint64_t* __restrict__ read_offsets, const uint64_t* __restrict__ win_offsets,
                       uint64_t num_reads, uint64_t* __restrict__ win_id, uint64_t* __restrict__ win_aux) {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint64_t hash_f[kBlock / 32][kTilePositions];
+    __shared__ uint64_t hash_r[kBlock / 32][kTilePositions];
+    __shared__ StreamQueue<W> queues[kBlock / 32];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t* hf = hash_f[wib];
+    uint64_t* hr = hash_r[wib];
+    StreamQueue<W>& q = queues[wib];
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t k = ix.k;
+    const uint32_t k = ix.k, m = ix.m, n = k - m + 1;
+    const uint64_t mmask = low_mask(2 * m), magic = ix.magic;
+    const bool canonical = ix.canonical != 0;
+    constexpr int NBLK = W == 1 ? 2 : 3;     // 32-character blocks a tile needs: 32 + k - 1 <= 62 / 94
+    uint32_t queued = 0;
     for (uint64_t r = warp; r < num_reads; r += nwarps) {
         const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
         if (len < k) continue;
         const uint64_t nwin = len - k + 1, w0 = win_offsets[r];
-        for (uint64_t i = lane; i < nwin; i += 32) {
-            const char* s = bases + b + i;
-            bool valid = true;
-            for (uint32_t j = 0; j < k; ++j) valid &= valid_base((uint8_t)s[j]);
-            uint64_t id = ~0ull, aux = 0;
+        const char* s = bases + b;
+        for (uint64_t wb = 0; wb < nwin; wb += 32) {
+            // ---- tile text: 2-bit packed words + invalid-character masks ------------------------------
+            uint64_t word[NBLK + 1];
+            uint32_t inval[NBLK];
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+                const uint64_t p = wb + 32 * blk + lane;
+                const uint8_t c = p < len ? (uint8_t)s[p] : (uint8_t)0;
+                word[blk] = pack_tile_word((c >> 1) & 3, lane);
+                inval[blk] = __ballot_sync(0xffffffffu, !valid_base(c));
+            }
+            word[NBLK] = 0;
+            const uint64_t w = wb + lane;
+            const Kmer<W> x = tile_kmer<W>(word[0], word[1], W == 1 ? 0 : word[2], lane, k);
+            // window valid <=> no invalid character among its k characters
+            bool valid = w < nwin;
+            {
+                const uint64_t v01 = ((uint64_t)inval[1] << 32) | inval[0];
+                uint64_t bad = (v01 >> lane) & low_mask(k < 64 - lane ? k : 64 - lane);
+                if (W == 2 && k + lane > 64) bad |= (uint64_t)inval[NBLK - 1] & low_mask(k + lane - 64);
+                valid = valid && bad == 0;
+            }
+            // ---- m-mer hashes of the tile, both strands (mixer_64::hash, hash_util.hpp:91) -------------
+            __syncwarp();
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+                const uint32_t p = 32 * blk + lane;
+                if (p < 32 + n - 1) {
+                    const uint64_t mm = funnel64(word[blk], word[blk + 1], lane) & mmask;
+                    hf[p] = (mm * SSHASH_MIX_C) ^ magic;
+                    hr[p] = (mmer_rc(mm, m) * SSHASH_MIX_C) ^ magic;
+                }
+            }
+            __syncwarp();
+            Minimizer mf{~0ull, 0}, mr{~0ull, 0};
+            Kmer<W> xr = x;
+            if (valid) {
+                uint64_t bf = ~0ull, br = ~0ull;
+                uint32_t pf = 0, pr = 0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint64_t a = hf[lane + i], c = hr[lane + i];
+                    if (a < bf) { bf = a; pf = i; }            // leftmost minimum of kmer
+                    if (c <= br) { br = c; pr = i; }           // rightmost here = leftmost of kmer_rc
+                }
+                xr = kmer_rc(x, k);
+                mf.pos = pf; mf.value = bf == ~0ull ? ~0ull : kmer_bits_at(x, pf, m);
+                // util.hpp:268-270: with no hash below UINT64_MAX the reference keeps (all ones, pos 0)
+                if (br == ~0ull) { mr.pos = 0; mr.value = ~0ull; }
+                else { mr.pos = n - 1 - pr; mr.value = kmer_bits_at(xr, mr.pos, m); }
+                if (bf == ~0ull) mf.pos = 0;
+            }
+            // ---- lookups ----------------------------------------------------------------------------
+            bool park = false;
+            if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = 0; }
             if (valid) {
                 LookupResult res;
-                lookup_kmer<W, false>(ix, pack_ascii<W>(s, k), true, res);
-                id = res.kmer_id;
-                aux = (1ull << 62) | (res.string_id & ((1ull << 62) - 1)) | (res.kmer_orientation < 0 ? (1ull << 63) : 0);
+                if (canonical) {                                // dictionary.cpp:24-42
+                    bool found;
+                    if (mf.value < mr.value) found = lookup_canonical_with<W, false>(ix, x, xr, mf, res);
+                    else if (mr.value < mf.value) found = lookup_canonical_with<W, false>(ix, x, xr, mr, res);
+                    else {
+                        found = lookup_canonical_with<W, false>(ix, x, xr, mf, res);
+                        if (!found) found = lookup_canonical_with<W, false>(ix, x, xr, mr, res);
+                    }
+                    store_window(win_id, win_aux, w0 + w, res, found && res.kmer_orientation < 0);
+                } else if (lookup_regular_with<W, false>(ix, x, mf, res)) {
+                    store_window(win_id, win_aux, w0 + w, res, false);
+                } else {
+                    park = true;
+                }
             }
-            win_id[w0 + i] = id;
-            win_aux[w0 + i] = aux;
+            if (canonical) continue;
+            const uint32_t mask = __ballot_sync(0xffffffffu, park);
+            if (park) q.put(queued + __popc(mask & ((1u << lane) - 1)), xr, mr, w0 + w);
+            queued += __popc(mask);
+            __syncwarp();
+            if (queued >= 32) {
+                queued -= 32;
+                const uint32_t e = queued + lane;
+                LookupResult res;
+                const bool found = lookup_regular_with<W, false>(ix, q.get(e), Minimizer{q.mini[e], q.pos[e]}, res);
+                store_window(win_id, win_aux, q.widx[e], res, found);
+                __syncwarp();
+            }
         }
+    }
+    if (!canonical && lane < queued) {
+        LookupResult res;
+        const bool found = lookup_regular_with<W, false>(ix, q.get(lane), Minimizer{q.mini[lane], q.pos[lane]}, res);
+        store_window(win_id, win_aux, q.widx[lane], res, found);
     }
 }
 
@@ -278,6 +427,37 @@ template <> struct KmerIter<2> {
     }
 };
 
+template <int W> struct RollingKmer;
+template <> struct RollingKmer<1> {
+    Kmer<1> x, xr;
+    __device__ void init(const char* s, uint32_t k) {      // first k-1 characters; push() adds the k-th
+        x.lo = 0; xr.lo = 0;
+        for (uint32_t i = 0; i + 1 < k; ++i) push((uint8_t)s[i], k);
+    }
+    __device__ void push(uint8_t c, uint32_t k) {
+        const uint64_t code = (c >> 1) & 3;
+        x.lo = (x.lo >> 2) | (code << (2 * (k - 1)));
+        xr.lo = ((xr.lo << 2) | (code ^ 2)) & low_mask(2 * k);
+    }
+};
+template <> struct RollingKmer<2> {
+    Kmer<2> x, xr;
+    __device__ void init(const char* s, uint32_t k) {
+        x.lo = x.hi = 0; xr.lo = xr.hi = 0;
+        for (uint32_t i = 0; i + 1 < k; ++i) push((uint8_t)s[i], k);
+    }
+    __device__ void push(uint8_t c, uint32_t k) {
+        const uint64_t code = (c >> 1) & 3;
+        x.lo = (x.lo >> 2) | (x.hi << 62);
+        x.hi >>= 2;
+        const uint32_t top = 2 * (k - 1);
+        if (top < 64) x.lo |= code << top; else x.hi |= code << (top - 64);
+        xr.hi = (xr.hi << 2) | (xr.lo >> 62);
+        xr.lo = (xr.lo << 2) | (code ^ 2);
+        if (2 * k <= 64) { xr.lo &= low_mask(2 * k); xr.hi = 0; } else xr.hi &= low_mask(2 * k - 64);
+    }
+};
+
 template <int W>
 __global__ void __launch_bounds__(kBlock)
 stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
@@ -295,7 +475,11 @@ stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restric
         uint64_t remaining = 0, cur_id = ~0ull;
         bool backward = false;
         KmerIter<W> it; it.at(0);
+        // rolling window k-mer and its reverse complement (streaming_query.hpp:68-80)
+        RollingKmer<W> roll;
+        roll.init(bases + b, k);
         for (uint64_t i = 0; i < nwin; ++i) {
+            roll.push((uint8_t)bases[b + i + k - 1], k);
             const uint64_t aux = win_aux[w0 + i];
             if (!(aux >> 62 & 1)) {                      // invalid window: reset() (streaming_query.hpp:59-65)
                 n_inv += 1; remaining = 0; cur_id = ~0ull;
@@ -304,7 +488,8 @@ stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restric
             }
             bool extended = false;
             if (remaining != 0) {                        // :88-99
-                Kmer<W> x = pack_ascii<W>(bases + b + i, k), xr = kmer_rc(x, k), e;
+                const Kmer<W> x = roll.x, xr = roll.xr;
+                Kmer<W> e;
                 if (!backward) { it.next(ix); e = it.get(ix); }
                 else { it.next_reverse(ix); e = it.get_reverse(ix); }
                 if (kmer_eq(e, x) || kmer_eq(e, xr)) {
