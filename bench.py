@@ -57,6 +57,25 @@ def rc_packed_torch(x, k: int):
     return (c >> s) & s64((1 << (64 - s)) - 1)
 
 
+def _rev2bit64(c):
+    for sh, m in ((2, 0x3333333333333333), (4, 0x0F0F0F0F0F0F0F0F), (8, 0x00FF00FF00FF00FF),
+                  (16, 0x0000FFFF0000FFFF), (32, 0x00000000FFFFFFFF)):
+        c = ((c >> sh) & s64(m)) | ((c & s64(m)) << sh)
+    return c
+
+
+def rc_packed_torch2(lo, hi, k: int):
+    """reverse complement of packed k<=63-mers held as two int64 words (kmer.hpp:159-165)."""
+    a = _rev2bit64(lo ^ s64(0xAAAAAAAAAAAAAAAA))     # becomes the HIGH word before the final shift
+    b = _rev2bit64(hi ^ s64(0xAAAAAAAAAAAAAAAA))     # becomes the LOW word
+    s = 128 - 2 * k
+    if s >= 64:
+        t = s - 64
+        return ((a >> t) & s64((1 << (64 - t)) - 1)) if t else a, a * 0
+    lsr = lambda v, n: (v >> n) & s64((1 << (64 - n)) - 1)
+    return lsr(b, s) | (a << (64 - s)), lsr(a, s)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"

@@ -35,7 +35,7 @@ def time_lookup(d, kmers, out, steps=5, warmup=3):
 def run(strings, length, k, m, canonical, queries, workdir, keep=False):
     import torch
     import sshash_b200
-    from bench import rc_packed_torch
+    from bench import rc_packed_torch, rc_packed_torch2
     import make_synth_index as msi
     from oracle import ref
     idx = os.path.join(workdir, "synth_%d_%d_k%d_m%d%s.sshash" % (strings, length, k, m, "_c" if canonical else ""))
@@ -43,7 +43,8 @@ def run(strings, length, k, m, canonical, queries, workdir, keep=False):
     if not os.path.exists(idx):
         fa = idx + ".fa"
         msi.write_fasta(fa, strings, length, 42)
-        ref.build(fa, k, m, idx, canonical=canonical, threads=len(os.sched_getaffinity(0)), tmp_dir=workdir)
+        ref.build(fa, k, m, idx, canonical=canonical, threads=len(os.sched_getaffinity(0)), tmp_dir=workdir,
+                  max_k=31 if k <= 31 else 63)
         os.remove(fa)
     build_s = time.time() - t0
     t0 = time.time()
@@ -62,11 +63,20 @@ def run(strings, length, k, m, canonical, queries, workdir, keep=False):
     assert torch.equal(out, ids)
     res["positive_forward"] = {"ms": ms, "lookups_per_s": n / ms * 1e3}
     mix = fwd.clone()
-    mix[1::2] = rc_packed_torch(mix[1::2], k)
+    if d.words == 1:
+        mix[1::2] = rc_packed_torch(mix[1::2], k)
+    else:
+        lo, hi = rc_packed_torch2(mix[1::2, 0], mix[1::2, 1], k)
+        mix[1::2, 0] = lo
+        mix[1::2, 1] = hi
     ms = time_lookup(d, mix, out)
     assert torch.equal(out, ids)
     res["positive_50rc"] = {"ms": ms, "lookups_per_s": n / ms * 1e3}
-    neg = torch.randint(0, 2 ** (2 * k), (n,), generator=gen, device=dev, dtype=torch.int64)
+    if d.words == 1:
+        neg = torch.randint(0, 2 ** (2 * k), (n,), generator=gen, device=dev, dtype=torch.int64)
+    else:
+        neg = torch.randint(0, 2 ** 62, (n, 2), generator=gen, device=dev, dtype=torch.int64)
+        neg[:, 1] &= (1 << (2 * k - 64)) - 1
     ms = time_lookup(d, neg, out)
     res["negative"] = {"ms": ms, "lookups_per_s": n / ms * 1e3, "found": int((out != -1).sum())}
     d.close()
