@@ -33,7 +33,12 @@ int main(int argc, char** argv) {
         auto r = dict.lookup(kmer.c_str());
         std::printf("access(0) = %s -> lookup id %lu orientation %ld string [%lu,%lu)\n", kmer.c_str(), r.kmer_id,
                     r.kmer_orientation, r.string_begin, r.string_end);
-        return bad == 0 && r.kmer_id == 0 ? 0 : 1;
+        dict.access(1, kmer.data());                       // k-mer 1 follows k-mer 0 in string 0
+        auto nb = dict.kmer_neighbours(kmer.c_str());
+        bool back_ok = false;
+        for (auto const& b : nb.backward) back_ok |= b.kmer_id == 0;
+        std::printf("kmer_neighbours(access(1)): backward contains id 0: %s\n", back_ok ? "yes" : "no");
+        return bad == 0 && r.kmer_id == 0 && back_ok ? 0 : 1;
     } catch (std::exception const& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -144,6 +144,22 @@ SSHASH_GPU_API int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const ui
                             uint64_t* kmers_out, void* stream);
 
 /*
+ * Navigational queries (include/dictionary.hpp:50-66, src/dictionary.cpp:112-201).  For each of the
+ * n inputs 8 results are produced: forward[A,C,T,G] then backward[A,C,T,G] (neighbourhood<Kmer>,
+ * include/util.hpp:77-81; alphabet order of include/kmer.hpp:115-119).  which: 1 =
+ * kmer_forward_neighbours, 2 = kmer_backward_neighbours, 3 = kmer_neighbours; slots not asked for
+ * hold the default lookup_result (not found), exactly like the reference's default-constructed
+ * arrays.  kmer_ids (nullable) and full (nullable) have 8*n entries.  String ids must be
+ * < num_strings.  With device buffers these two calls synchronise `stream` before returning.
+ */
+SSHASH_GPU_API int sshash_gpu_kmer_neighbours_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n,
+                                                    int check_reverse_complement, int which, uint64_t* kmer_ids,
+                                                    sshash_lookup_result* full, void* stream);
+SSHASH_GPU_API int sshash_gpu_string_neighbours_batch(const sshash_gpu_dict* dict, const uint64_t* string_ids, uint64_t n,
+                                                      int check_reverse_complement, uint64_t* kmer_ids,
+                                                      sshash_lookup_result* full, void* stream);
+
+/*
  * Streaming membership over a batch of reads: replaces streaming_query<Dict,canonical>::lookup
  * driven per read as in streaming_query_from_fastq_file (include/streaming_query.hpp:56-115,
  * src/query.cpp:78-108): reset per read, reads shorter than k skipped, a window containing a

@@ -34,6 +34,8 @@ def lib():
         l.oracle_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         l.oracle_lookup_batch_ascii.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         l.oracle_access_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        l.oracle_kmer_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        l.oracle_string_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         l.oracle_streaming_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                              C.POINTER(Report)]
         _lib = l
@@ -88,6 +90,19 @@ class OracleDictionary:
         out = np.empty(ids.size * self.words, dtype=np.uint64)
         lib().oracle_access_batch(self.h, ids.ctypes.data, ids.size, out.ctypes.data)
         return out if self.words == 1 else out.reshape(-1, 2)
+
+    def kmer_neighbours(self, kmers, check_rc: bool = True, which: int = 3):
+        a = np.ascontiguousarray(kmers, dtype=np.uint64)
+        n = a.size // self.words
+        out = np.empty((n, 8), dtype=RESULT_DTYPE)
+        lib().oracle_kmer_neighbours_batch(self.h, a.ctypes.data, n, int(check_rc), which, out.ctypes.data)
+        return out
+
+    def string_neighbours(self, string_ids, check_rc: bool = True):
+        ids = np.ascontiguousarray(string_ids, dtype=np.uint64)
+        out = np.empty((ids.size, 8), dtype=RESULT_DTYPE)
+        lib().oracle_string_neighbours_batch(self.h, ids.ctypes.data, ids.size, int(check_rc), out.ctypes.data)
+        return out
 
     def streaming_reads(self, bases: bytes, offsets, full: bool = False):
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)

@@ -76,6 +76,8 @@ def _lib(max_k: int):
         lib.ref_lookup_batch_ascii.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p,
                                                C.c_void_p]
         lib.ref_access_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.ref_kmer_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        lib.ref_string_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.ref_streaming_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(Report),
                                            C.POINTER(C.c_double)]
         lib.ref_streaming_reads.restype = C.c_double
@@ -151,6 +153,19 @@ class RefDictionary:
         out = np.empty(ids.size * self.words, dtype=np.uint64)
         self.lib.ref_access_batch(self.h, ids.ctypes.data, ids.size, out.ctypes.data)
         return out if self.words == 1 else out.reshape(-1, 2)
+
+    def kmer_neighbours(self, kmers, check_rc: bool = True, which: int = 3):
+        """(n, 8) lookup_result records: forward[A,C,T,G], backward[A,C,T,G]."""
+        a, n = self._kmers(kmers)
+        out = np.empty((n, 8), dtype=RESULT_DTYPE)
+        self.lib.ref_kmer_neighbours_batch(self.h, a.ctypes.data, n, int(check_rc), which, out.ctypes.data)
+        return out
+
+    def string_neighbours(self, string_ids, check_rc: bool = True):
+        ids = np.ascontiguousarray(string_ids, dtype=np.uint64)
+        out = np.empty((ids.size, 8), dtype=RESULT_DTYPE)
+        self.lib.ref_string_neighbours_batch(self.h, ids.ctypes.data, ids.size, int(check_rc), out.ctypes.data)
+        return out
 
     def streaming_file(self, path: str, multiline: bool = False):
         rep = Report()

@@ -14,6 +14,8 @@
  *   ref_info             k(), m(), canonical(), num_kmers(), ... (include/dictionary.hpp:31-38)
  *   ref_lookup_batch     dictionary::lookup(Kmer, check_rc)      (src/dictionary.cpp:64-78)
  *   ref_access_batch     dictionary::access                      (src/dictionary.cpp:90-94)
+ *   ref_kmer_neighbours_batch / ref_string_neighbours_batch
+ *                        dictionary::kmer_neighbours etc.        (src/dictionary.cpp:112-201)
  *   ref_streaming_file   dictionary::streaming_query_from_file   (src/query.cpp:118-175)
  *   ref_streaming_reads  streaming_query<>::lookup per read      (include/streaming_query.hpp:56-109)
  */
@@ -187,6 +189,35 @@ void ref_access_batch(void* h, const uint64_t* ids, uint64_t n, uint64_t* kmers_
     for (uint64_t i = 0; i != n; ++i) {
         d->access(ids[i], s.data());
         store_kmer(kmers_out, i, util::string_to_uint_kmer<default_kmer_t>(s.data(), k));
+    }
+}
+
+/* which: 1 = kmer_forward_neighbours, 2 = kmer_backward_neighbours, 3 = kmer_neighbours.
+   out: 8 records per k-mer: forward[A,C,T,G] then backward[A,C,T,G] (include/util.hpp:77-81). */
+void ref_kmer_neighbours_batch(void* h, const uint64_t* kmers, uint64_t n, int check_rc, int which,
+                               ref_lookup_result* out) {
+    auto* d = static_cast<dictionary_type*>(h);
+    for (uint64_t i = 0; i != n; ++i) {
+        auto x = load_kmer(kmers, i);
+        neighbourhood<default_kmer_t> nb = which == 1   ? d->kmer_forward_neighbours(x, check_rc != 0)
+                                           : which == 2 ? d->kmer_backward_neighbours(x, check_rc != 0)
+                                                        : d->kmer_neighbours(x, check_rc != 0);
+        for (int j = 0; j != 4; ++j) {
+            copy_result(out + 8 * i + j, nb.forward[j]);
+            copy_result(out + 8 * i + 4 + j, nb.backward[j]);
+        }
+    }
+}
+
+void ref_string_neighbours_batch(void* h, const uint64_t* string_ids, uint64_t n, int check_rc,
+                                 ref_lookup_result* out) {
+    auto* d = static_cast<dictionary_type*>(h);
+    for (uint64_t i = 0; i != n; ++i) {
+        auto nb = d->string_neighbours(string_ids[i], check_rc != 0);
+        for (int j = 0; j != 4; ++j) {
+            copy_result(out + 8 * i + j, nb.forward[j]);
+            copy_result(out + 8 * i + 4 + j, nb.backward[j]);
+        }
     }
 }
 

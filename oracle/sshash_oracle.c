@@ -527,6 +527,42 @@ void oracle_lookup_batch_ascii(const oracle_dict* d, const char* kmers, uint64_t
 }
 
 /* ------------------------------------------------------------------------------------------
+ * navigational queries: dictionary::kmer_forward/backward_neighbours, kmer_neighbours,
+ * string_neighbours (src/dictionary.cpp:112-201).  Alphabet order A,C,T,G = codes 0..3
+ * (include/kmer.hpp:115-119,194).  Slots that the reference leaves default-constructed keep the
+ * default lookup_result (invalid ids, minimizer_found = true, util.hpp:39-49).
+ * ---------------------------------------------------------------------------------------- */
+static void neighbours_from(const oracle_dict* d, u128 suffix, int do_fwd, u128 prefix, int do_bwd, int check_rc,
+                            oracle_result* out /* 8 */) {
+    for (int j = 0; j != 8; ++j) result_init(out + j, 1);
+    if (do_fwd)                                              /* forward_neighbours, dictionary.cpp:112-120 */
+        for (u128 c = 0; c != 4; ++c) lookup(d, suffix | (c << (2 * (d->k - 1))), check_rc, out + (int)c);
+    if (do_bwd)                                              /* backward_neighbours, dictionary.cpp:121-129 */
+        for (u128 c = 0; c != 4; ++c) lookup(d, prefix | c, check_rc, out + 4 + (int)c);
+}
+
+void oracle_kmer_neighbours_batch(const oracle_dict* d, const uint64_t* kmers, uint64_t n, int check_rc, int which,
+                                  oracle_result* out) {
+    for (uint64_t i = 0; i != n; ++i) {
+        u128 x = load_kmer(d, kmers, i);
+        u128 suffix = x >> 2;                                               /* get_suffix: drop_char, :139-143 */
+        u128 prefix = (x << 2) & mask_bits((unsigned)(2 * d->k));           /* get_prefix: pad_char + take_chars(k), :160-165 */
+        neighbours_from(d, suffix, which & 1, prefix, which & 2, check_rc, out + 8 * i);
+    }
+}
+
+/* string_neighbours dictionary.cpp:189-201 with string_prefix / string_suffix spss.hpp:19-27 */
+void oracle_string_neighbours_batch(const oracle_dict* d, const uint64_t* string_ids, uint64_t n, int check_rc,
+                                    oracle_result* out) {
+    for (uint64_t i = 0; i != n; ++i) {
+        uint64_t begin = ends_access(&d->ends, string_ids[i]), end = ends_access(&d->ends, string_ids[i] + 1);
+        u128 suffix = read_kmer_at(d, d->k - 1, 2 * (end - d->k + 1));
+        u128 prefix = read_kmer_at(d, d->k - 1, 2 * begin) << 2;
+        neighbours_from(d, suffix, 1, prefix, 1, check_rc, out + 8 * i);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Access: offsets::id_to_offset offsets.hpp:41-65 (binary search restated without the linear
  * tail) + spss::access spss.hpp:114-118
  * ---------------------------------------------------------------------------------------- */

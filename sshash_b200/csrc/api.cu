@@ -47,6 +47,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     void* d_in = nullptr; uint64_t in_cap = 0;
     void* d_out = nullptr; uint64_t out_cap = 0;
+    void* d_tmp = nullptr; uint64_t tmp_cap = 0;
 };
 
 // Device scratch owned by one call at a time (taken from / returned to the dictionary's pool).
@@ -67,6 +68,7 @@ struct Workspace {
         for (auto& s : slots) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
+            if (s.d_tmp) cudaFree(s.d_tmp);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         cudaFree(d_bases); cudaFree(d_read_offsets); cudaFree(d_win_offsets); cudaFree(d_block_sums);
@@ -496,6 +498,60 @@ int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_id
                        [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
                            return launch_access(ix, sms, static_cast<const uint64_t*>(in), cn, static_cast<uint64_t*>(out), s);
                        });
+}
+
+// kmer_neighbours / string_neighbours: n inputs -> 8n results (forward A,C,T,G then backward A,C,T,G)
+static int neighbours_common(const sshash_gpu_dict* dict, const uint64_t* in, bool strings, uint64_t n, int check_rc, int which,
+                             uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!in || (!kmer_ids && !full) || which < 1 || which > 3) return fail(SSHASH_GPU_EINVAL, "bad argument");
+    const DeviceIndex& ix = dict->ix;
+    const LaunchCtx& ctx = dict->ctx;
+    const uint64_t W = ix.kmer_words, in_elem = strings ? 8 : 8 * W;
+    const bool rc = check_rc != 0;
+    const bool dev = is_device_pointer(in);
+    if ((kmer_ids && dev != is_device_pointer(kmer_ids)) || (full && dev != is_device_pointer(full)))
+        return fail(SSHASH_GPU_EINVAL, "inputs and outputs must all be host or all be device pointers");
+    WorkspaceLease ws(dict);
+    if (dev) {
+        Slot& s = ws->slots[0];
+        CU(ensure_slot(s, 0, 0));
+        CU(ensure(s.d_tmp, s.tmp_cap, 8 * n * W * 8));
+        cudaStream_t cs = static_cast<cudaStream_t>(stream);
+        CU(launch_neighbours(ix, ctx, in, strings, n, rc, which, static_cast<uint64_t*>(s.d_tmp), kmer_ids, full, cs));
+        CU(cudaStreamSynchronize(cs));      // the expansion scratch belongs to the workspace
+        return SSHASH_GPU_OK;
+    }
+    const uint64_t out_elem = full ? 8 * sizeof(sshash_lookup_result) : 8 * 8;
+    const uint64_t chunk = std::max<uint64_t>(1, (32ull << 20) / out_elem);
+    uint8_t* out = full ? reinterpret_cast<uint8_t*>(full) : reinterpret_cast<uint8_t*>(kmer_ids);
+    int c = 0;
+    for (uint64_t off = 0; off < n; off += chunk, ++c) {
+        const uint64_t cn = std::min(chunk, n - off);
+        Slot& s = ws->slots[c % Workspace::kSlots];
+        CU(ensure_slot(s, chunk * in_elem, chunk * out_elem));
+        CU(ensure(s.d_tmp, s.tmp_cap, 8 * chunk * W * 8));
+        CU(cudaMemcpyAsync(s.d_in, reinterpret_cast<const uint8_t*>(in) + off * in_elem, cn * in_elem, cudaMemcpyHostToDevice, s.stream));
+        CU(launch_neighbours(ix, ctx, static_cast<const uint64_t*>(s.d_in), strings, cn, rc, which, static_cast<uint64_t*>(s.d_tmp),
+                             full ? nullptr : static_cast<uint64_t*>(s.d_out),
+                             full ? static_cast<sshash_lookup_result*>(s.d_out) : nullptr, s.stream));
+        CU(cudaMemcpyAsync(out + off * out_elem, s.d_out, cn * out_elem, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : ws->slots) if (s.stream) CU(cudaStreamSynchronize(s.stream));
+    if (full && kmer_ids) for (uint64_t i = 0; i != 8 * n; ++i) kmer_ids[i] = full[i].kmer_id;
+    return SSHASH_GPU_OK;
+}
+
+int sshash_gpu_kmer_neighbours_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                                     int which, uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+    return neighbours_common(dict, kmers, false, n, check_reverse_complement, which, kmer_ids, full, stream);
+}
+
+int sshash_gpu_string_neighbours_batch(const sshash_gpu_dict* dict, const uint64_t* string_ids, uint64_t n,
+                                       int check_reverse_complement, uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+    return neighbours_common(dict, string_ids, true, n, check_reverse_complement, 3, kmer_ids, full, stream);
 }
 
 // One device-resident batch of reads: offsets scan, window lookups, state-machine replay.

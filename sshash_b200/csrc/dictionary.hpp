@@ -9,6 +9,8 @@
 //   lookup_result lookup(Kmer, bool = true)               lookup(kmer_t)  (dictionary.hpp:42, dictionary.cpp:64-78)
 //   bool is_member(char const* / Kmer, bool = true)       same            (dictionary.hpp:75-76)
 //   void access(uint64_t kmer_id, char* string_kmer)      same            (dictionary.hpp:71)
+//   kmer_neighbours / kmer_forward_neighbours /           same            (dictionary.hpp:50-66, dictionary.cpp:112-201)
+//     kmer_backward_neighbours / string_neighbours
 //   streaming_query_from_file(filename, multiline)        same            (dictionary.hpp:81-82)
 //   -- callers that loop over lookup (tools/perf.hpp:55-60, test/check.hpp:29-31) --
 //                                                         lookup_batch / is_member_batch / access_batch
@@ -118,6 +120,30 @@ public:
         check(sshash_gpu_access_batch(m_dict, kmer_ids, n, kmers_out, stream));
     }
 
+    /* Navigational queries (include/dictionary.hpp:50-66): forward[A,C,T,G] then backward[A,C,T,G]. */
+    struct neighbourhood { lookup_result forward[4]; lookup_result backward[4]; };   // include/util.hpp:77-81
+    neighbourhood kmer_neighbours(kmer_t uint_kmer, bool check_reverse_complement = true) const {
+        return neighbours_of(uint_kmer, check_reverse_complement, 3);
+    }
+    neighbourhood kmer_forward_neighbours(kmer_t uint_kmer, bool check_reverse_complement = true) const {
+        return neighbours_of(uint_kmer, check_reverse_complement, 1);
+    }
+    neighbourhood kmer_backward_neighbours(kmer_t uint_kmer, bool check_reverse_complement = true) const {
+        return neighbours_of(uint_kmer, check_reverse_complement, 2);
+    }
+    neighbourhood kmer_neighbours(char const* string_kmer, bool check_reverse_complement = true) const {
+        return neighbours_of(string_to_uint_kmer(string_kmer, k()), check_reverse_complement, 3);
+    }
+    neighbourhood string_neighbours(uint64_t string_id, bool check_reverse_complement = true) const {
+        neighbourhood nb;
+        check(sshash_gpu_string_neighbours_batch(m_dict, &string_id, 1, check_reverse_complement, nullptr, nb.forward, nullptr));
+        return nb;
+    }
+    void kmer_neighbours_batch(uint64_t const* kmers, uint64_t n, uint64_t* kmer_ids /* 8n */, bool check_reverse_complement = true,
+                               int which = 3, lookup_result* full = nullptr, void* stream = nullptr) const {
+        check(sshash_gpu_kmer_neighbours_batch(m_dict, kmers, n, check_reverse_complement, which, kmer_ids, full, stream));
+    }
+
     /* Streaming membership. */
     streaming_query_report streaming_query_from_file(std::string const& filename, bool multiline = false) const {
         streaming_query_report r;
@@ -132,6 +158,13 @@ public:
     }
 
 private:
+    neighbourhood neighbours_of(kmer_t x, bool check_rc, int which) const {
+        static_assert(sizeof(neighbourhood) == 8 * sizeof(lookup_result), "neighbourhood must be 8 packed records");
+        uint64_t w[2] = {x.lo, x.hi};
+        neighbourhood nb;
+        check(sshash_gpu_kmer_neighbours_batch(m_dict, w, 1, check_rc, which, nullptr, nb.forward, nullptr));
+        return nb;
+    }
     static void check(int status) {
         if (status != SSHASH_GPU_OK) throw std::runtime_error(sshash_gpu_last_error());
     }

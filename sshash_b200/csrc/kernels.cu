@@ -152,6 +152,65 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------------
+// navigational queries (src/dictionary.cpp:112-201): a neighbourhood is 8 lookups -- the k-1
+// suffix extended by A,C,T,G (forward) and the k-1 prefix preceded by A,C,T,G (backward); alphabet
+// order "ACTG" = codes 0..3 (include/kmer.hpp:115-119,194).  These kernels only EXPAND the 8 query
+// k-mers per input; the lookups themselves run in lookup_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Kmer<1> with_last(Kmer<1> suffix, uint32_t c, uint32_t k) { return {suffix.lo | ((uint64_t)c << (2 * (k - 1)))}; }
+__device__ __forceinline__ Kmer<2> with_last(Kmer<2> suffix, uint32_t c, uint32_t k) {
+    const uint32_t s = 2 * (k - 1);
+    if (s < 64) suffix.lo |= (uint64_t)c << s; else suffix.hi |= (uint64_t)c << (s - 64);
+    return suffix;
+}
+__device__ __forceinline__ Kmer<1> drop_first(Kmer<1> x) { return {x.lo >> 2}; }                       // get_suffix :139-143
+__device__ __forceinline__ Kmer<2> drop_first(Kmer<2> x) { return {(x.lo >> 2) | (x.hi << 62), x.hi >> 2}; }
+__device__ __forceinline__ Kmer<1> pad_first(Kmer<1> x, uint32_t k) { return {(x.lo << 2) & low_mask(2 * k)}; }   // get_prefix :160-165
+__device__ __forceinline__ Kmer<2> pad_first(Kmer<2> x, uint32_t k) {
+    Kmer<2> r{x.lo << 2, (x.hi << 2) | (x.lo >> 62)};
+    if (2 * k <= 64) { r.lo &= low_mask(2 * k); r.hi = 0; } else r.hi &= low_mask(2 * k - 64);
+    return r;
+}
+__device__ __forceinline__ Kmer<1> or_first(Kmer<1> x, uint32_t c) { return {x.lo | c}; }
+__device__ __forceinline__ Kmer<2> or_first(Kmer<2> x, uint32_t c) { return {x.lo | c, x.hi}; }
+
+template <int W, bool STRINGS>
+__global__ void __launch_bounds__(kBlock)
+expand_neighbours_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ in, uint64_t n,
+                         uint64_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t k = ix.k;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 8 * n; t += stride) {
+        const uint64_t i = t >> 3;
+        const uint32_t j = (uint32_t)t & 7;
+        Kmer<W> suffix, prefix;
+        if (STRINGS) {                                   // string_neighbours :189-201, spss.hpp:19-27
+            const uint64_t sid = in[i];
+            const uint64_t begin = ld64<true>(ix.ends + sid), end = ld64<true>(ix.ends + sid + 1);
+            suffix = read_kmer(ix, end - k + 1, k - 1, (Kmer<W>*)nullptr);
+            prefix = pad_first(read_kmer(ix, begin, k - 1, (Kmer<W>*)nullptr), k);
+        } else {
+            const Kmer<W> x = load_kmer<W>(in, i);
+            suffix = drop_first(x);
+            prefix = pad_first(x, k);
+        }
+        store_kmer(out, t, j < 4 ? with_last(suffix, j, k) : or_first(prefix, j - 4));
+    }
+}
+
+// slots the reference leaves default-constructed (e.g. backward[] of kmer_forward_neighbours)
+__global__ void __launch_bounds__(kBlock)
+reset_neighbour_slots_kernel(uint64_t n, int which, uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 8 * n; t += stride) {
+        const bool fwd_slot = (t & 7) < 4;
+        if ((fwd_slot && (which & 1)) || (!fwd_slot && (which & 2))) continue;
+        if (ids) ids[t] = ~0ull;
+        if (full) { LookupResult r; result_clear(r, true); store_full(full, t, r); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // batched dictionary::access: offsets::id_to_offset (include/offsets.hpp:41-65) restated as a
 // binary search over the decoded end-points for the last string whose first k-mer id
 // (= begin - string_id * (k-1)) is <= id, then spss::access (spss.hpp:114-118).
@@ -670,6 +729,25 @@ cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
     const int grid = grid_for(n, ctx.sm_count, 8);
     if (ix.kmer_words == 1) return launch(access_kernel<1>, grid, stream, ctx, ix, ids, n, kmers_out);
     return launch(access_kernel<2>, grid, stream, ctx, ix, ids, n, kmers_out);
+}
+
+cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* in, bool strings, uint64_t n,
+                              bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(8 * n, ctx.sm_count, 8);
+    cudaError_t e;
+    if (ix.kmer_words == 1)
+        e = strings ? launch(expand_neighbours_kernel<1, true>, grid, stream, ctx, ix, in, n, expanded)
+                    : launch(expand_neighbours_kernel<1, false>, grid, stream, ctx, ix, in, n, expanded);
+    else
+        e = strings ? launch(expand_neighbours_kernel<2, true>, grid, stream, ctx, ix, in, n, expanded)
+                    : launch(expand_neighbours_kernel<2, false>, grid, stream, ctx, ix, in, n, expanded);
+    if (e != cudaSuccess) return e;
+    e = launch_lookup(ix, ctx, expanded, false, 8 * n, check_rc, ids, full, nullptr, stream);
+    if (e != cudaSuccess) return e;
+    if ((which & 3) != 3) e = launch(reset_neighbour_slots_kernel, grid, stream, ctx, n, which, ids, full);
+    return e;
 }
 
 uint64_t window_offsets_scratch_words(uint64_t num_reads) { return (num_reads + 1 + kScanTile - 1) / kScanTile + 1; }

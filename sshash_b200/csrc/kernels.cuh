@@ -32,6 +32,13 @@ cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const voi
 cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
                           cudaStream_t stream);
 
+// Navigational queries: expand n inputs (packed k-mers, or string ids when strings = true) into 8n
+// neighbour k-mers in `expanded` (8n * kmer_words words), look them up, reset the slots `which`
+// (bit 0 forward, bit 1 backward) does not ask for.
+cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* in, bool strings, uint64_t n,
+                              bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
+                              cudaStream_t stream);
+
 // win_offsets[r] = number of windows in reads [0, r), computed on the device from read_offsets
 cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
                                   uint64_t* block_sums, cudaStream_t stream);

@@ -184,6 +184,25 @@ class Dictionary:
         x = int(w[0]) | (int(w[1]) << 64 if self.words == 2 else 0)
         return uint_kmer_to_string(x, self.k())
 
+    # ---- navigational queries, include/dictionary.hpp:50-66 ------------------------------------
+    def kmer_neighbours_batch(self, kmers, check_reverse_complement: bool = True, which: int = 3, full: bool = True):
+        """Batched kmer_neighbours (which=3), kmer_forward_neighbours (1), kmer_backward_neighbours (2):
+        (n, 8) results per k-mer = forward[A,C,T,G] + backward[A,C,T,G]; host (numpy) buffers."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        n = self._count(kmers)
+        out = np.empty((n, 8), dtype=RESULT_DTYPE if full else np.uint64)
+        check(self._lib.sshash_gpu_kmer_neighbours_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), which,
+                                                         None if full else _ptr(out), _ptr(out) if full else None, None))
+        return out
+
+    def string_neighbours_batch(self, string_ids, check_reverse_complement: bool = True, full: bool = True):
+        string_ids = np.ascontiguousarray(string_ids, dtype=np.uint64)
+        out = np.empty((string_ids.size, 8), dtype=RESULT_DTYPE if full else np.uint64)
+        check(self._lib.sshash_gpu_string_neighbours_batch(self._h, _ptr(string_ids), string_ids.size,
+                                                           int(check_reverse_complement), None if full else _ptr(out),
+                                                           _ptr(out) if full else None, None))
+        return out
+
     # ---- streaming, include/streaming_query.hpp + src/query.cpp -------------------------------
     def streaming_batch(self, bases, read_offsets, want_ids: bool = True, stream: int = 0):
         """Streaming membership over a batch of reads (concatenated characters + offsets).

@@ -139,8 +139,29 @@ def synth_reads(d, rng, nreads, read_len=150):
     return reads
 
 
+def make_nav(name, lib):
+    """navigational-query goldens (src/dictionary.cpp:112-201): kmer_neighbours for the first 400
+    golden queries (positives, fwd and RC, + negatives at the tail) and string_neighbours of the
+    first 40 strings, complete lookup_result records from the reference."""
+    idx = os.path.join(HERE, name + ".sshash")
+    d = ref.RefDictionary(idx, max_k=lib)
+    z = np.load(os.path.join(HERE, name + ".npz"))
+    q = z["queries"].reshape(-1, d.words)
+    sel = np.concatenate([q[:300], q[-100:]]).reshape(-1)
+    sid = np.arange(min(40, d.num_strings), dtype=np.uint64)
+    np.savez_compressed(os.path.join(HERE, name + ".nav.npz"), kmers=sel,
+                        both=d.kmer_neighbours(sel, which=3), forward=d.kmer_neighbours(sel, which=1),
+                        backward=d.kmer_neighbours(sel, which=2), both_norc=d.kmer_neighbours(sel, check_rc=False),
+                        string_ids=sid, strings=d.string_neighbours(sid))
+    d.close()
+
+
 def main():
     os.makedirs(TMP, exist_ok=True)
+    if "--nav-only" in sys.argv:
+        for name, _src, _k, _m, _canon, _nseq, lib in FIXTURES:
+            make_nav(name, lib)
+        return
     manifest = {}
     for name, src, k, m, canon, nseq, lib in FIXTURES:
         fa = os.path.join(TMP, name + ".fa")
@@ -172,6 +193,7 @@ def main():
                               num_found=int((ids != 2**64 - 1).sum()))
         print(name, manifest[name])
         d.close()
+        make_nav(name, lib)
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

@@ -150,6 +150,32 @@ def test_streaming_device_buffers_and_file(dicts, name, tmp_path):
     assert d.streaming_query_from_file(str(tmp_path / "x.txt"))["num_kmers"] == 0  # unsupported extension
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_navigational_queries(dicts, name):
+    """kmer_neighbours / forward / backward / string_neighbours vs the reference's goldens, and the
+    property of test/check_from_file.hpp:173-226: consecutive k-mers of a string are neighbours."""
+    from conftest import GOLDEN
+    g, d = golden(name), dicts(name)
+    z = np.load(os.path.join(GOLDEN, name + ".nav.npz"))
+    for key, which, rc in (("both", 3, True), ("forward", 1, True), ("backward", 2, True), ("both_norc", 3, False)):
+        got = d.kmer_neighbours_batch(z["kmers"], check_reverse_complement=rc, which=which)
+        for f in got.dtype.names:
+            assert (got[f] == z[key][f]).all(), (key, f)
+        ids = d.kmer_neighbours_batch(z["kmers"], check_reverse_complement=rc, which=which, full=False)
+        assert (ids == z[key]["kmer_id"]).all()
+    got = d.string_neighbours_batch(z["string_ids"])
+    for f in got.dtype.names:
+        assert (got[f] == z["strings"][f]).all(), f
+    # id i and id i+1 inside one string: the successor is a forward neighbour, the predecessor a backward one
+    ids = np.arange(0, 2000, dtype=np.uint64)
+    km = d.access_batch(ids)
+    full = d.lookup_batch(km.reshape(-1), full=True)
+    nb = d.kmer_neighbours_batch(km.reshape(-1), full=False)
+    same = full["string_id"][1:] == full["string_id"][:-1]
+    assert ((nb[:-1, :4] == ids[1:, None]).any(axis=1) | ~same).all()
+    assert ((nb[1:, 4:] == ids[:-1, None]).any(axis=1) | ~same).all()
+
+
 def test_edge_cases(dicts):
     d = dicts("se_k31_m13")
     assert d.lookup_batch(np.zeros(0, dtype=np.uint64)).size == 0

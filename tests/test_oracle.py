@@ -87,6 +87,22 @@ def test_lookup_access_roundtrip(oracles, name):
     assert (full["kmer_id_in_string"] == full["kmer_offset"] - full["string_begin"]).all()
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_navigational_queries_match_reference_golden(oracles, name):
+    """kmer_neighbours / forward / backward / string_neighbours (src/dictionary.cpp:112-201)."""
+    import os
+    from conftest import GOLDEN
+    o = oracles(name)
+    z = np.load(os.path.join(GOLDEN, name + ".nav.npz"))
+    for key, which, rc in (("both", 3, True), ("forward", 1, True), ("backward", 2, True), ("both_norc", 3, False)):
+        got = o.kmer_neighbours(z["kmers"], check_rc=rc, which=which)
+        for f in got.dtype.names:
+            assert (got[f] == z[key][f]).all(), (key, f)
+    got = o.string_neighbours(z["string_ids"])
+    for f in got.dtype.names:
+        assert (got[f] == z["strings"][f]).all(), f
+
+
 def test_bad_files(tmp_path):
     p = tmp_path / "bad.sshash"
     p.write_bytes(b"\x04\x01\x01" + b"\0" * 100)
