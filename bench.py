@@ -164,6 +164,20 @@ def scale_workload():
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
+def streaming_workload():
+    """BASELINE.json configs[2]: streaming membership over 1e6 synthetic 150-bp reads (50 % hit) on
+    the cfg-1 index; windows/s device-resident and through the C ABI with host buffers, checked
+    against the C oracle on the first 20000 reads."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import stream_bench
+        r = stream_bench.run(INDEX, 1_000_000)
+        r["workload"] = "cfg3: 1e6 synthetic 150-bp reads (1.2e8 windows), 50 % of reads from the index, cfg-1 index"
+        return r
+    except Exception as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -255,6 +269,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     n = args.queries
@@ -370,6 +385,7 @@ def main():
             line["gather"] = gather
         if world == 1 and not args.no_scale:
             line["scale"] = scale_workload()
+            line["streaming"] = streaming_workload()
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             sample = h_in_np[:CPU_SAMPLE]

@@ -61,6 +61,7 @@ struct Workspace {
     uint64_t* d_block_sums = nullptr; uint64_t bs_cap = 0;
     uint64_t* d_win_id = nullptr; uint64_t* d_win_aux = nullptr; uint64_t win_cap = 0;
     uint64_t* d_ids = nullptr; uint64_t ids_cap = 0;
+    void* d_anchors = nullptr; uint64_t anchors_cap = 0;
     unsigned long long* d_counters = nullptr;
     unsigned long long* h_counters = nullptr;   // pinned
 
@@ -72,7 +73,7 @@ struct Workspace {
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         cudaFree(d_bases); cudaFree(d_read_offsets); cudaFree(d_win_offsets); cudaFree(d_block_sums);
-        cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters);
+        cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters); cudaFree(d_anchors);
         if (h_counters) cudaFreeHost(h_counters);
     }
 };
@@ -568,8 +569,12 @@ static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const cha
         CU(cudaMalloc(reinterpret_cast<void**>(&w.d_win_aux), bytes));
         w.win_cap = bytes;
     }
+    // SSHASH_GPU_STREAM_ALIGN=0 disables the anchor/alignment shortcut (every window is looked up)
+    static const bool use_anchors = !(std::getenv("SSHASH_GPU_STREAM_ALIGN") && std::getenv("SSHASH_GPU_STREAM_ALIGN")[0] == '0');
+    if (use_anchors) CU(ensure(w.d_anchors, w.anchors_cap, streaming_anchor_bytes(num_reads)));
     CU(launch_window_offsets(ix.k, d_read_offsets, num_reads, w.d_win_offsets, w.d_block_sums, s));
-    CU(launch_streaming(ix, dict->ctx, d_bases, d_read_offsets, w.d_win_offsets, num_reads, w.d_win_id, w.d_win_aux,
+    CU(launch_streaming(ix, dict->ctx, d_bases, d_read_offsets, w.d_win_offsets, num_reads, use_anchors ? w.d_anchors : nullptr,
+                        w.d_win_id, w.d_win_aux,
                         d_ids_out, w.d_counters, s));
     return SSHASH_GPU_OK;
 }

@@ -306,30 +306,117 @@ __device__ __forceinline__ uint64_t kmer_bits_at(Kmer<2> x, uint32_t pos, uint32
     return w & low_mask(2 * m);
 }
 
+// ------------------------------------------------------------------------------------------------
+// streaming membership, step 0: ANCHORS.  Reads that come from the indexed strings are resolved
+// without per-window lookups: a few sample windows per read (kAnchorsPerRead) are looked up here,
+// one thread each; a positive sample fixes an ungapped alignment of the whole read against one
+// string ("diagonal"), and stream_windows_kernel then only has to compare each window's k-mer with
+// the string's k-mer at the aligned offset -- the same final comparison a lookup performs
+// (spss.hpp:222,259-261), minus minimizer, MPHF and bucket.  A window whose aligned comparison
+// succeeds inside the string holds the k-mer with id  offset - string_id*(k-1); because the index
+// stores every (canonical) k-mer once -- SSHash's input contract, README "without duplicate
+// k-mers" -- that is the id dictionary::lookup returns for it.  Windows that do not match (read
+// errors, other strings, absent k-mers) fall through to the regular per-window lookup.
+//   forward alignment:  read base t <-> string base diag + t
+//   backward alignment: read base t <-> complement of string base diag - t
+// ------------------------------------------------------------------------------------------------
+constexpr int kAnchorsPerRead = 3;
+struct Anchor { int64_t diag; uint64_t info; };   // info: bit 63 valid, bit 62 backward, low 62 bits string id
+
+template <int W>
+__global__ void __launch_bounds__(kBlock, 4)
+stream_anchor_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
+                     const uint64_t* __restrict__ read_offsets, uint64_t num_reads, Anchor* __restrict__ anchors) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t k = ix.k;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < num_reads * kAnchorsPerRead; t += stride) {
+        const uint64_t r = t / kAnchorsPerRead, s = t % kAnchorsPerRead;
+        const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
+        Anchor a{0, 0};
+        if (len >= k) {
+            const uint64_t nwin = len - k + 1, p = s * (nwin / kAnchorsPerRead);
+            const char* q = bases + b + p;
+            bool valid = true;
+            for (uint32_t j = 0; j < k; ++j) valid &= valid_base((uint8_t)q[j]);
+            if (valid) {
+                LookupResult res;
+                lookup_kmer<W, false>(ix, pack_ascii<W>(q, k), true, res);
+                if (res.kmer_id != ~0ull) {
+                    const bool back = res.kmer_orientation < 0;
+                    a.diag = back ? (int64_t)(res.kmer_offset + k - 1 + p) : (int64_t)res.kmer_offset - (int64_t)p;
+                    a.info = (1ull << 63) | (back ? (1ull << 62) : 0) | res.string_id;
+                }
+            }
+        }
+        anchors[t] = a;
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(kBlock, 4)
 stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
                       const uint64_t* __restrict__ read_offsets, const uint64_t* __restrict__ win_offsets,
-                      uint64_t num_reads, uint64_t* __restrict__ win_id, uint64_t* __restrict__ win_aux) {
+                      uint64_t num_reads, const Anchor* __restrict__ anchors, uint64_t* __restrict__ win_id,
+                      uint64_t* __restrict__ win_aux, unsigned long long* __restrict__ next_read) {
     __shared__ uint64_t hash_f[kBlock / 32][kTilePositions];
     __shared__ uint64_t hash_r[kBlock / 32][kTilePositions];
     __shared__ StreamQueue<W> queues[kBlock / 32];
+    __shared__ int64_t anchor_s[kBlock / 32][kAnchorsPerRead][4];   // diag, string begin, string end, sid | flags
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t* hf = hash_f[wib];
     uint64_t* hr = hash_r[wib];
     StreamQueue<W>& q = queues[wib];
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t k = ix.k, m = ix.m, n = k - m + 1;
     const uint64_t mmask = low_mask(2 * m), magic = ix.magic;
     const bool canonical = ix.canonical != 0;
     constexpr int NBLK = W == 1 ? 2 : 3;     // 32-character blocks a tile needs: 32 + k - 1 <= 62 / 94
     uint32_t queued = 0;
-    for (uint64_t r = warp; r < num_reads; r += nwarps) {
+    // Reads cost very different amounts of work (a read resolved by its anchor is ~10x cheaper than a
+    // read whose every window needs a lookup), so warps claim reads dynamically, kReadsPerClaim at a time.
+    constexpr uint64_t kReadsPerClaim = 8;
+    for (;;) {
+        uint64_t claim = 0;
+        if (lane == 0) claim = atomicAdd(next_read, (unsigned long long)kReadsPerClaim);
+        claim = __shfl_sync(0xffffffffu, claim, 0);
+        if (claim >= num_reads) break;
+        const uint64_t claim_end = claim + kReadsPerClaim < num_reads ? claim + kReadsPerClaim : num_reads;
+    for (uint64_t r = claim; r < claim_end; ++r) {
         const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
         if (len < k) continue;
         const uint64_t nwin = len - k + 1, w0 = win_offsets[r];
         const char* s = bases + b;
+        // this read's distinct alignments, kept in shared memory (warp-uniform data)
+        bool any_back = false, any_anchor = false;
+        if (anchors) {
+            __syncwarp();
+            bool ok = false, back = false;
+            int64_t diag = 0;
+            uint64_t sid = 0;
+            if (lane < kAnchorsPerRead) {
+                const Anchor a = anchors[r * kAnchorsPerRead + lane];
+                ok = (a.info >> 63) != 0;
+                back = (a.info >> 62 & 1) != 0;
+                diag = a.diag;
+                sid = a.info & ((1ull << 62) - 1);
+            }
+#pragma unroll
+            for (int aj = 0; aj < kAnchorsPerRead - 1; ++aj) {   // same string + diagonal + strand = same alignment
+                const bool ok_j = __shfl_sync(0xffffffffu, ok, aj), back_j = __shfl_sync(0xffffffffu, back, aj);
+                const int64_t diag_j = __shfl_sync(0xffffffffu, diag, aj);
+                const uint64_t sid_j = __shfl_sync(0xffffffffu, sid, aj);
+                if ((int)lane > aj && ok_j && back_j == back && diag_j == diag && sid_j == sid) ok = false;
+            }
+            if (lane < kAnchorsPerRead) {
+                int64_t* a = anchor_s[wib][lane];
+                a[0] = diag;
+                a[1] = ok ? (int64_t)ld64<true>(ix.ends + sid) : 0;
+                a[2] = ok ? (int64_t)ld64<true>(ix.ends + sid + 1) : 0;
+                a[3] = (int64_t)(sid | (ok ? 1ull << 63 : 0) | (back ? 1ull << 62 : 0));
+            }
+            any_anchor = __ballot_sync(0xffffffffu, ok) != 0;
+            any_back = __ballot_sync(0xffffffffu, ok && back) != 0;
+            __syncwarp();
+        }
         for (uint64_t wb = 0; wb < nwin; wb += 32) {
             // ---- tile text: 2-bit packed words + invalid-character masks ------------------------------
             uint64_t word[NBLK + 1];
@@ -352,6 +439,33 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                 if (W == 2 && k + lane > 64) bad |= (uint64_t)inval[NBLK - 1] & low_mask(k + lane - 64);
                 valid = valid && bad == 0;
             }
+            // ---- windows resolved by an anchor's alignment: one k-mer comparison, no lookup ---------------
+            Kmer<W> xr = x;
+            bool have_xr = false;
+            if (any_anchor) {
+                bool resolved = false;
+                if (any_back) { xr = kmer_rc(x, k); have_xr = true; }
+#pragma unroll
+                for (int ai = 0; ai < kAnchorsPerRead; ++ai) {
+                    const int64_t* a = anchor_s[wib][ai];
+                    const uint64_t info = (uint64_t)a[3];
+                    if (!(info >> 63)) continue;         // warp-uniform
+                    const bool back = (info >> 62 & 1) != 0;
+                    const uint64_t sid = info & ((1ull << 62) - 1);
+                    const int64_t oj = back ? a[0] - (int64_t)w - (int64_t)(k - 1) : a[0] + (int64_t)w;
+                    if (valid && !resolved && oj >= a[1] && oj + (int64_t)k <= a[2]) {
+                        const Kmer<W> sk = read_kmer(ix, (uint64_t)oj, k, (Kmer<W>*)nullptr);
+                        if (kmer_eq(sk, back ? xr : x)) {
+                            resolved = true;
+                            win_id[w0 + w] = (uint64_t)oj - sid * (k - 1);
+                            win_aux[w0 + w] = (1ull << 62) | sid | (back ? (1ull << 63) : 0);
+                        }
+                    }
+                }
+                if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = 0; }
+                valid = valid && !resolved;              // from here on: windows that still need a lookup
+                if (__ballot_sync(0xffffffffu, valid) == 0) continue;
+            } else if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = 0; }
             // ---- m-mer hashes of the tile, both strands (mixer_64::hash, hash_util.hpp:91) -------------
             __syncwarp();
 #pragma unroll
@@ -365,7 +479,6 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
             }
             __syncwarp();
             Minimizer mf{~0ull, 0}, mr{~0ull, 0};
-            Kmer<W> xr = x;
             if (valid) {
                 uint64_t bf = ~0ull, br = ~0ull;
                 uint32_t pf = 0, pr = 0;
@@ -374,7 +487,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                     if (a < bf) { bf = a; pf = i; }            // leftmost minimum of kmer
                     if (c <= br) { br = c; pr = i; }           // rightmost here = leftmost of kmer_rc
                 }
-                xr = kmer_rc(x, k);
+                if (!have_xr) xr = kmer_rc(x, k);
                 mf.pos = pf; mf.value = bf == ~0ull ? ~0ull : kmer_bits_at(x, pf, m);
                 // util.hpp:268-270: with no hash below UINT64_MAX the reference keeps (all ones, pos 0)
                 if (br == ~0ull) { mr.pos = 0; mr.value = ~0ull; }
@@ -383,7 +496,6 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
             }
             // ---- lookups ----------------------------------------------------------------------------
             bool park = false;
-            if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = 0; }
             if (valid) {
                 LookupResult res;
                 if (canonical) {                                // dictionary.cpp:24-42
@@ -415,6 +527,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                 __syncwarp();
             }
         }
+    }
     }
     if (!canonical && lane < queued) {
         LookupResult res;
@@ -750,6 +863,8 @@ cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const
     return e;
 }
 
+uint64_t streaming_anchor_bytes(uint64_t num_reads) { return num_reads * kAnchorsPerRead * sizeof(Anchor); }
+
 uint64_t window_offsets_scratch_words(uint64_t num_reads) { return (num_reads + 1 + kScanTile - 1) / kScanTile + 1; }
 
 cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
@@ -763,17 +878,28 @@ cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint
 }
 
 cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
-                             const uint64_t* win_offsets, uint64_t num_reads, uint64_t* win_id, uint64_t* win_aux,
+                             const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
                              uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream) {
     if (num_reads == 0) return cudaSuccess;
+    Anchor* an = static_cast<Anchor*>(anchors);
+    if (an) {
+        const int grid = grid_for(num_reads * kAnchorsPerRead, ctx.sm_count, 8);
+        cudaError_t e = ix.kmer_words == 1 ? launch(stream_anchor_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, num_reads, an)
+                                           : launch(stream_anchor_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, num_reads, an);
+        if (e != cudaSuccess) return e;
+    }
     {
         uint64_t threads = num_reads * 32;
-        const int grid = grid_for(threads, ctx.sm_count, 8);
+        const int grid = grid_for(threads, ctx.sm_count, 4);
+        cudaError_t ez = cudaMemsetAsync(counters + 5, 0, sizeof(unsigned long long), stream);   // work-claim counter
+        if (ez != cudaSuccess) return ez;
         cudaError_t e;
         if (ix.kmer_words == 1)
-            e = launch(stream_windows_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
+            e = launch(stream_windows_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads,
+                       (const Anchor*)an, win_id, win_aux, counters + 5);
         else
-            e = launch(stream_windows_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux);
+            e = launch(stream_windows_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads,
+                       (const Anchor*)an, win_id, win_aux, counters + 5);
         if (e != cudaSuccess) return e;
     }
     {

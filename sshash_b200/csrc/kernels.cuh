@@ -47,7 +47,9 @@ uint64_t window_offsets_scratch_words(uint64_t num_reads);
 // Streaming membership over a batch of reads: per-window lookups, then the per-read replay of the
 // reference state machine.  counters[5] += {num_kmers, searches, extensions, negative, invalid}.
 cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
-                             const uint64_t* win_offsets, uint64_t num_reads, uint64_t* win_id, uint64_t* win_aux,
+                             const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
                              uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream);
+// scratch for the per-read alignment anchors (pass nullptr as `anchors` to look every window up)
+uint64_t streaming_anchor_bytes(uint64_t num_reads);
 
 }  // namespace sshash_b200
