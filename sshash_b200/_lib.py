@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsshash_gpu.so")
+# SSHASH_GPU_LIB: A/B builds of the same library during kernel work (tools/, not the product default)
+LIB_PATH = os.environ.get("SSHASH_GPU_LIB") or os.path.join(_HERE, "libsshash_gpu.so")
 
 STATUS = {0: "OK", 1: "EINVAL", 2: "EIO", 3: "EFORMAT", 4: "EVERSION", 5: "ECUDA", 6: "ENOMEM"}
 

@@ -280,6 +280,37 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     d->ctx.hot_base = slab;
     d->ctx.hot_bytes = slab_bytes;
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
+
+    // FINGERPRINTED CODEWORDS: the control codewords are re-encoded on the device as a compact vector
+    // of width w + f whose entries carry, above the reference's w-bit codeword, an f-bit fingerprint
+    // of the minimizer that owns the slot (read back from `strings` through the bucket).  A minimizer
+    // that is not in the index hashes to an arbitrary slot; the ids-only lookup rejects it right
+    // after the codeword read, without the strings read the reference needs to find out.  The
+    // verbatim copy is dropped afterwards.  SSHASH_GPU_FP=0 keeps the verbatim vector.
+    ix.cw_code_bits = ix.codewords.width;
+    ix.cw_fp_bits = 0;
+    const char* fp_env = std::getenv("SSHASH_GPU_FP");
+    if (!(fp_env && fp_env[0] == '0') && ix.codewords.size && ix.codewords.width + 8 <= 57) {
+        const uint32_t w = ix.codewords.width;
+        const uint32_t fpb = w + 8 <= 32 ? 32 - w : 8;            // round the entry up to 32 bits when that is cheap
+        const uint64_t words = (ix.codewords.size * (uint64_t)(w + fpb) + 63) / 64;
+        uint64_t* fresh = nullptr;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&fresh), words * 8 + kPadBytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fingerprinted codewords)");
+        CU(cudaMemset(fresh, 0, words * 8 + kPadBytes));
+        CU(launch_build_fingerprints(ix, d->ctx, fpb, fresh, nullptr));
+        CU(cudaDeviceSynchronize());
+        void* old = const_cast<uint64_t*>(ix.codewords.data);
+        d->allocs.erase(std::find(d->allocs.begin(), d->allocs.end(), old));
+        cudaFree(old);
+        d->allocs.push_back(fresh);
+        up.bytes += words * 8 - f.control_codewords.data.bytes();
+        ix.codewords.data = fresh;
+        ix.codewords.width = w + fpb;
+        ix.codewords.mask = (w + fpb) >= 64 ? ~0ull : ((1ull << (w + fpb)) - 1);
+        ix.cw_fp_bits = fpb;
+    }
+    if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
     d->info.device_bytes = up.bytes;
     return SSHASH_GPU_OK;
 }

@@ -9,7 +9,11 @@
 //   free_slots     u32[]  every partition's Elias-Fano free-slot list DECODED to plain integers
 //                         (replaces elias_fano::access + darray select: one 4-byte load)
 //   phf_parts      DevPhfPart[] per-partition constants + offsets into the two pools above
-//   codewords      u64[]  control_codewords compact vector, verbatim
+//   codewords      u64[]  control_codewords compact vector, RE-ENCODED at open time: entry =
+//                         codeword | fingerprint(minimizer owning the slot) << cw_code_bits.  A
+//                         minimizer that is NOT in the index hashes to an arbitrary slot, and all but
+//                         2^-cw_fp_bits of those are rejected right after this read, before the cold
+//                         strings read the reference needs to find out (verbatim when cw_fp_bits == 0)
 //   mid_load       u64[]  mid_load_buckets compact vector, verbatim
 //   heavy          u64[]  heavy_load_buckets compact vector, verbatim
 //   skew_pos[i]    u64[]  positions[i] compact vectors, verbatim
@@ -79,6 +83,8 @@ struct DeviceIndex {
     uint64_t n_ends;
     const uint32_t* ends_dir;
     uint32_t begin_buckets_of_size[65];
+    uint32_t cw_code_bits;     // width of the reference's codeword inside a `codewords` entry
+    uint32_t cw_fp_bits;       // fingerprint bits above it (0 = verbatim vector)
     uint32_t pad_;
 };
 
@@ -215,7 +221,7 @@ struct Minimizer { uint64_t value; uint32_t pos; };
 // fits 32 bits and the 64-bit multiply by the mixer constant needs two IMADs instead of four.
 // If no hash is < UINT64_MAX the reference leaves minimizer = all ones, pos = 0 (util.hpp:268-270).
 template <bool SMALL_M>
-__device__ __forceinline__ Minimizer compute_minimizer(Kmer<1> x, uint32_t k, uint32_t m, uint64_t magic) {
+__device__ __noinline__ Minimizer compute_minimizer_exact(Kmer<1> x, uint32_t k, uint32_t m, uint64_t magic) {
     uint64_t min_hash = ~0ull, v = x.lo;
     uint32_t pos = 0;
     const uint32_t n = k - m + 1;
@@ -241,7 +247,7 @@ __device__ __forceinline__ Minimizer compute_minimizer(Kmer<1> x, uint32_t k, ui
     return {mini, pos};
 }
 template <bool SMALL_M>
-__device__ __forceinline__ Minimizer compute_minimizer(Kmer<2> x, uint32_t k, uint32_t m, uint64_t magic) {
+__device__ __noinline__ Minimizer compute_minimizer_exact(Kmer<2> x, uint32_t k, uint32_t m, uint64_t magic) {
     uint64_t min_hash = ~0ull, lo = x.lo, hi = x.hi;
     uint32_t pos = 0;
     const uint32_t n = k - m + 1;
@@ -260,9 +266,65 @@ __device__ __forceinline__ Minimizer compute_minimizer(Kmer<2> x, uint32_t k, ui
     if (min_hash == ~0ull) mini = ~0ull;
     return {mini, pos};
 }
+
+// FAST PATH.  x -> (x * C) mod 2^64 is a bijection (C is odd), so two m-mers have equal hashes only
+// if they are equal; the scan therefore compares only the HIGH 32 bits of each hash -- which needs
+// the high half of the product only, one xor, one 32-bit compare -- and raises `tie` whenever a
+// hash's high half equals the running minimum's.  Any m-mer whose high half ties with the final
+// minimum's raises it (whichever comes first sets the minimum, the other one hits the equality),
+// and only then (a repeated m-mer, or a 2^-32 accident) the exact 64-bit scan above runs.  The
+// m-mers are cut out of the k-mer's 32-bit words with one funnel shift each, 16 per word.
+__device__ __forceinline__ void kmer_words32(Kmer<1> x, uint32_t (&r)[4]) {
+    r[0] = (uint32_t)x.lo; r[1] = (uint32_t)(x.lo >> 32); r[2] = 0; r[3] = 0;
+}
+__device__ __forceinline__ void kmer_words32(Kmer<2> x, uint32_t (&r)[4]) {
+    r[0] = (uint32_t)x.lo; r[1] = (uint32_t)(x.lo >> 32); r[2] = (uint32_t)x.hi; r[3] = (uint32_t)(x.hi >> 32);
+}
+__device__ __forceinline__ uint64_t kmer_bits_at(Kmer<1> x, uint32_t s) { return x.lo >> s; }
+__device__ __forceinline__ uint64_t kmer_bits_at(Kmer<2> x, uint32_t s) {   // s < 128
+    return s == 0 ? x.lo : (s < 64 ? ((x.lo >> s) | (x.hi << (64 - s))) : (x.hi >> (s - 64)));
+}
+
+template <int W, bool SMALL_M>
+__device__ __forceinline__ Minimizer compute_minimizer_fast(Kmer<W> x, uint32_t k, uint32_t m, uint64_t magic) {
+    const uint32_t n = k - m + 1;
+    const uint32_t c_lo = (uint32_t)SSHASH_MIX_C, c_hi = (uint32_t)(SSHASH_MIX_C >> 32);
+    const uint32_t magic_hi = (uint32_t)(magic >> 32);
+    const uint32_t mm = SMALL_M ? (uint32_t)low_mask(2 * m) : (uint32_t)low_mask(2 * m - 32);
+    uint32_t r[4];
+    kmer_words32(x, r);
+    uint32_t min_hi = 0xffffffffu, pos = 0;
+    bool tie = false;
+    for (uint32_t base = 0; base < n; base += 16) {
+        const uint32_t cnt = n - base < 16 ? n - base : 16;
+#pragma unroll 4
+        for (uint32_t j = 0; j < cnt; ++j) {
+            uint32_t hh;
+            if (SMALL_M) {
+                const uint32_t w = __funnelshift_r(r[0], r[1], 2 * j) & mm;
+                hh = __umulhi(w, c_lo) + w * c_hi;
+            } else {
+                const uint32_t wl = __funnelshift_r(r[0], r[1], 2 * j);
+                const uint32_t wh = __funnelshift_r(r[1], r[2], 2 * j) & mm;
+                hh = __umulhi(wl, c_lo) + wl * c_hi + wh * c_lo;
+            }
+            hh ^= magic_hi;
+            tie |= hh == min_hi;
+            if (hh < min_hi) { min_hi = hh; pos = base + j; }
+        }
+        r[0] = r[1]; r[1] = r[2]; r[2] = r[3]; r[3] = 0;
+    }
+    if (tie) return compute_minimizer_exact<SMALL_M>(x, k, m, magic);
+    return {kmer_bits_at(x, 2 * pos) & low_mask(2 * m), pos};
+}
+
 template <int W>
 __device__ __forceinline__ Minimizer compute_minimizer(Kmer<W> x, uint32_t k, uint32_t m, uint64_t magic) {
-    return m <= 16 ? compute_minimizer<true>(x, k, m, magic) : compute_minimizer<false>(x, k, m, magic);
+#ifdef SSHASH_EXACT_MINIMIZER_ONLY   // A/B switch for measurements
+    return m <= 16 ? compute_minimizer_exact<true>(x, k, m, magic) : compute_minimizer_exact<false>(x, k, m, magic);
+#else
+    return m <= 16 ? compute_minimizer_fast<W, true>(x, k, m, magic) : compute_minimizer_fast<W, false>(x, k, m, magic);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,15 +409,32 @@ __device__ __forceinline__ void result_clear(LookupResult& r, bool minimizer_fou
 __device__ __forceinline__ Hash128 skew_hash(const DevPhf& f, Kmer<1> x) { return city_hash_u64(f, x.lo); }
 __device__ __forceinline__ Hash128 skew_hash(const DevPhf& f, Kmer<2> x) { return city_hash_u128(f, x.lo, x.hi); }
 
+// Fingerprint of a minimizer (cw_fp_bits <= 32 bits).  In a canonical index the text at a bucket
+// offset may hold the reverse complement of the minimizer (compute_minimizer_tuples.cpp:76-86), so
+// the fingerprint is taken of the smaller of the two forms there.
+__device__ __forceinline__ uint32_t minimizer_fingerprint(const DeviceIndex& ix, uint64_t minimizer) {
+    if (ix.canonical) { uint64_t r = mmer_rc(minimizer, ix.m); minimizer = r < minimizer ? r : minimizer; }
+    return (((uint32_t)minimizer ^ (uint32_t)(minimizer >> 32)) * 0x9e3779b1u) >> (32 - ix.cw_fp_bits);
+}
+
 // sparse_and_skew_index::lookup (sparse_and_skew_index.hpp:112-137): minimizer -> bucket.
 // Returns the number of offsets in the bucket; `first` = the single offset (SINGLETON/HEAVYLOAD)
 // or the index of the first entry in mid_load_buckets (MIDLOAD).
-template <int W>
+// USE_FP: reject a minimizer whose slot belongs to a different minimizer (returns 0 = no bucket).
+// Only the ids-only paths may use it: a full lookup_result needs the bucket type of the (wrong)
+// slot to reproduce minimizer_found (spss.hpp:51-65).
+template <int W, bool USE_FP>
 __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t minimizer, Kmer<W> skew_key,
                                               uint64_t& first, bool& heavy) {
+    uint32_t fp = 0;
+    if (USE_FP) fp = minimizer_fingerprint(ix, minimizer);   // before the loads: only 32 bits stay live across them
     uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
     uint64_t code = compact_get<false>(ix.codewords, id);
     heavy = false;
+    if (ix.cw_fp_bits) {
+        if (USE_FP && (uint32_t)(code >> ix.cw_code_bits) != fp) return 0;
+        code &= low_mask(ix.cw_code_bits);
+    }
     if ((code & 1) == 0) { first = code >> 1; return 1; }                         // SINGLETON
     if ((code & 3) == 1) {                                                        // MIDLOAD
         code >>= 2;
@@ -388,7 +467,8 @@ template <int W, bool FULL>
 __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<W> x, Minimizer mi, LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     uint64_t first; bool heavy;
-    uint32_t n = bucket_of<W>(ix, mi.value, x, first, heavy);
+    uint32_t n = bucket_of<W, !FULL>(ix, mi.value, x, first, heavy);
+    if (!FULL && n == 0) { result_clear(res, false); return false; }
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {
         if (read_mmer(ix, off0, m) != mi.value) { result_clear(res, heavy); return false; }
@@ -427,7 +507,8 @@ __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kme
     const uint32_t k = ix.k, m = ix.m;
     Kmer<W> canon = kmer_lt(x, xr) ? x : xr;            // std::min(uint_kmer, uint_kmer_rc), dictionary.cpp:53
     uint64_t first; bool heavy;
-    uint32_t n = bucket_of<W>(ix, mi.value, canon, first, heavy);
+    uint32_t n = bucket_of<W, !FULL>(ix, mi.value, canon, first, heavy);
+    if (!FULL && n == 0) { result_clear(res, false); return false; }
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {
         uint64_t rm = read_mmer(ix, off0, m);
@@ -460,24 +541,31 @@ __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kme
     return false;
 }
 
-// dictionary::lookup(Kmer, check_reverse_complement), src/dictionary.cpp:64-78 (+ :24-42)
+// dictionary::lookup_canonical(Kmer), src/dictionary.cpp:24-42
+template <int W, bool FULL>
+__device__ __forceinline__ bool lookup_canonical(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
+    const uint32_t k = ix.k;
+    Kmer<W> xr = kmer_rc(x, k);
+    Minimizer mf = compute_minimizer(x, k, ix.m, ix.magic);
+    Minimizer mr = compute_minimizer(xr, k, ix.m, ix.magic);
+    // the smaller minimizer decides; on a tie the forward info is tried first, then the rc info (:35-41)
+    const bool tie = mf.value == mr.value;
+    Minimizer mi = mr.value < mf.value ? mr : mf;
+#pragma unroll 1
+    for (int t = 0;; ++t) {                             // one inlined copy of the pass
+        if (lookup_canonical_with<W, FULL>(ix, x, xr, mi, res)) return true;
+        if (!tie || t == 1) return false;
+        mi = mr;
+    }
+}
+
+// dictionary::lookup(Kmer, check_reverse_complement), src/dictionary.cpp:64-78
 template <int W, bool FULL>
 __device__ __forceinline__ void lookup_kmer(const DeviceIndex& ix, Kmer<W> x, bool check_rc, LookupResult& res) {
-    const uint32_t k = ix.k;
-    if (ix.canonical) {
-        Kmer<W> xr = kmer_rc(x, k);
-        Minimizer mf = compute_minimizer(x, k, ix.m, ix.magic);
-        Minimizer mr = compute_minimizer(xr, k, ix.m, ix.magic);
-        if (mf.value < mr.value) { lookup_canonical_with<W, FULL>(ix, x, xr, mf, res); }
-        else if (mr.value < mf.value) { lookup_canonical_with<W, FULL>(ix, x, xr, mr, res); }
-        else {
-            if (!lookup_canonical_with<W, FULL>(ix, x, xr, mf, res)) lookup_canonical_with<W, FULL>(ix, x, xr, mr, res);
-        }
-        return;
-    }
+    if (ix.canonical) { lookup_canonical<W, FULL>(ix, x, res); return; }
     if (lookup_regular<W, FULL>(ix, x, res)) return;
     if (check_rc) {
-        lookup_regular<W, FULL>(ix, kmer_rc(x, k), res);
+        lookup_regular<W, FULL>(ix, kmer_rc(x, ix.k), res);
         res.kmer_orientation = -1;                      // dictionary.cpp:74-75: also for a miss
     }
 }

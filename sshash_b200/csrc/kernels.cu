@@ -97,7 +97,11 @@ template <> struct RcQueue<2> {
     __device__ Kmer<2> get(uint32_t s) const { return {lo[s], hi[s]}; }
 };
 
-template <int W, int MODE, bool ASCII, int MINB>
+// The loop has ONE lookup call site: each trip a warp takes either 32 fresh queries or, as soon as
+// 32 are parked (or the input is exhausted), 32 parked reverse complements.  CANON selects the
+// canonical (src/dictionary.cpp:24-56) or the regular (:7-22, :64-78) flow at compile time so that
+// each instantiation carries only its own path.
+template <int W, int MODE, bool ASCII, bool CANON, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
               uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
@@ -106,48 +110,78 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
     RcQueue<W>& q = queues[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t k = ix.k;
-    const bool two_pass = !ix.canonical && check_rc != 0;
+    const bool two_pass = !CANON && check_rc != 0;
     uint32_t queued = 0;                                  // warp-uniform
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-    for (uint64_t tile = first; tile < n; tile += stride) {   // warp-uniform trip count
-        const uint64_t i = tile + lane;
-        bool park = false;
+    uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    for (;;) {                                            // warp-uniform control flow
+        const bool fresh = tile < n && queued < 32;
+        if (!fresh && queued == 0) break;
         Kmer<W> x{};
-        if (i < n) {
-            if (ASCII) x = pack_ascii<W>(static_cast<const char*>(queries) + i * k, k);
-            else x = load_kmer<W>(static_cast<const uint64_t*>(queries), i);
-            LookupResult r;
-            if (!two_pass) {
-                lookup_kmer<W, FULL>(ix, x, false, r);    // canonical, or regular without the RC retry
-                emit<MODE>(i, r, ids, full, member);
-            } else if (lookup_regular<W, FULL>(ix, x, r)) {
-                emit<MODE>(i, r, ids, full, member);
-            } else {
-                park = true;
+        uint64_t i;
+        bool active;
+        if (fresh) {
+            i = tile + lane;
+            tile += stride;
+            active = i < n;
+            if (active) {
+                if (ASCII) x = pack_ascii<W>(static_cast<const char*>(queries) + i * k, k);
+                else x = load_kmer<W>(static_cast<const uint64_t*>(queries), i);
             }
+        } else {                                          // the parked reverse complements, newest first
+            const uint32_t cnt = queued < 32 ? queued : 32;
+            queued -= cnt;
+            active = lane < cnt;
+            x = q.get(queued + lane);
+            i = q.idx[queued + lane];
+            __syncwarp();
         }
-        if (!two_pass) continue;
-        const uint32_t mask = __ballot_sync(0xffffffffu, park);
-        if (park) q.put(queued + __popc(mask & ((1u << lane) - 1)), kmer_rc(x, k), i);
-        queued += __popc(mask);
-        __syncwarp();
-        if (queued >= 32) {
-            queued -= 32;
-            LookupResult r;
-            const uint64_t qi = q.idx[queued + lane];
-            lookup_regular<W, FULL>(ix, q.get(queued + lane), r);
-            r.kmer_orientation = -1;                      // dictionary.cpp:74-75 (also for a miss)
-            emit<MODE>(qi, r, ids, full, member);
+        bool found = false;
+        LookupResult r;
+        if (active) {
+            if (CANON) found = lookup_canonical<W, FULL>(ix, x, r);
+            else found = lookup_regular<W, FULL>(ix, x, r);
+        }
+        const bool park = active && fresh && two_pass && !found;
+        if (active && !park) {
+            if (!CANON && !fresh) r.kmer_orientation = -1;    // dictionary.cpp:74-75 (also for a miss)
+            emit<MODE>(i, r, ids, full, member);
+        }
+        if (fresh && two_pass) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, park);
+            if (park) q.put(queued + __popc(mask & ((1u << lane) - 1)), kmer_rc(x, k), i);
+            queued += __popc(mask);
             __syncwarp();
         }
     }
-    if (two_pass && lane < queued) {                      // drain
-        LookupResult r;
-        const uint64_t qi = q.idx[lane];
-        lookup_regular<W, FULL>(ix, q.get(lane), r);
-        r.kmer_orientation = -1;
-        emit<MODE>(qi, r, ids, full, member);
+}
+
+// ------------------------------------------------------------------------------------------------
+// open-time re-encoding of the control codewords with minimizer fingerprints: one thread per MPHF
+// slot reads the slot's codeword from the verbatim vector (still in ix.codewords, cw_fp_bits == 0),
+// follows it to the first offset of its bucket (sparse_and_skew_index.hpp:112-137), fingerprints the
+// m-mer found there in `strings` and ORs  codeword | fp << w  into the zeroed output vector.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+build_fingerprints_kernel(const __grid_constant__ DeviceIndex ix, uint32_t fp_bits, unsigned long long* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t w = ix.codewords.width, wo = w + fp_bits;
+    DeviceIndex fx = ix;                      // only canonical / m / cw_fp_bits are read by the fingerprint
+    fx.cw_fp_bits = fp_bits;
+    for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < ix.codewords.size; id += stride) {
+        const uint64_t entry = compact_get<false>(ix.codewords, id);
+        uint64_t code = entry, off;
+        if ((code & 1) == 0) off = code >> 1;
+        else if ((code & 3) == 1) {
+            code >>= 2;
+            const uint32_t size = (uint32_t)(code & 63) + 2;
+            off = compact_get<false>(ix.mid_load, ix.begin_buckets_of_size[size] + (code >> 6) * size);
+        } else off = compact_get<false>(ix.heavy, code >> 5);           // (code >> 2) >> 3 = begin of the heavy bucket
+        const uint64_t v = entry | ((uint64_t)minimizer_fingerprint(fx, read_mmer(ix, off, ix.m)) << w);
+        const uint64_t pos = id * wo, word = pos >> 6;
+        const uint32_t s = (uint32_t)pos & 63u;
+        atomicOr(out + word, (unsigned long long)(v << s));
+        if (s + wo > 64) atomicOr(out + word + 1, (unsigned long long)(v >> (64 - s)));
     }
 }
 
@@ -822,7 +856,8 @@ cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const voi
     const int crc = check_rc ? 1 : 0;
     cudaError_t err = cudaSuccess;
 #define SSHASH_LAUNCH(W, MODE, ASCII) \
-    err = launch(lookup_kernel<W, MODE, ASCII, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
+    err = ix.canonical ? launch(lookup_kernel<W, MODE, ASCII, true, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member) \
+                       : launch(lookup_kernel<W, MODE, ASCII, false, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
 #define SSHASH_DISPATCH_MODE(W, ASCII)                     \
     do {                                                   \
         if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);         \
@@ -861,6 +896,13 @@ cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const
     if (e != cudaSuccess) return e;
     if ((which & 3) != 3) e = launch(reset_neighbour_slots_kernel, grid, stream, ctx, n, which, ids, full);
     return e;
+}
+
+cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
+                                      cudaStream_t stream) {
+    if (ix.codewords.size == 0) return cudaSuccess;
+    return launch(build_fingerprints_kernel, grid_for(ix.codewords.size, ctx.sm_count, 8), stream, ctx, ix, fp_bits,
+                  reinterpret_cast<unsigned long long*>(out));
 }
 
 uint64_t streaming_anchor_bytes(uint64_t num_reads) { return num_reads * kAnchorsPerRead * sizeof(Anchor); }

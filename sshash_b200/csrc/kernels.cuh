@@ -39,6 +39,11 @@ cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const
                               bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
                               cudaStream_t stream);
 
+// open time: re-encode ix.codewords (verbatim) into `out` (zeroed, width + fp_bits per entry) with
+// a fingerprint of each slot's minimizer above the codeword
+cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
+                                      cudaStream_t stream);
+
 // win_offsets[r] = number of windows in reads [0, r), computed on the device from read_offsets
 cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
                                   uint64_t* block_sums, cudaStream_t stream);

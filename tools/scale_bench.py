@@ -32,13 +32,15 @@ def time_lookup(d, kmers, out, steps=5, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-def run(strings, length, k, m, canonical, queries, workdir, keep=False):
+def run(strings, length, k, m, canonical, queries, workdir, keep=False, index=None):
     import torch
     import sshash_b200
     from bench import rc_packed_torch, rc_packed_torch2
     import make_synth_index as msi
     from oracle import ref
     idx = os.path.join(workdir, "synth_%d_%d_k%d_m%d%s.sshash" % (strings, length, k, m, "_c" if canonical else ""))
+    if index:
+        idx, keep = index, True
     t0 = time.time()
     if not os.path.exists(idx):
         fa = idx + ".fa"
@@ -50,6 +52,7 @@ def run(strings, length, k, m, canonical, queries, workdir, keep=False):
     t0 = time.time()
     d = sshash_b200.Dictionary(idx)
     open_s = time.time() - t0
+    k = d.k()
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev).manual_seed(7)
     n = queries
@@ -95,10 +98,11 @@ def main():
     ap.add_argument("--queries", type=int, default=100_000_000)
     ap.add_argument("--workdir", default=None)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--index", default=None, help="use this existing index instead of building a synthetic one")
     args = ap.parse_args()
     wd = args.workdir or tempfile.mkdtemp(prefix="sshash_scale_")
     os.makedirs(wd, exist_ok=True)
-    print(json.dumps(run(args.strings, args.length, args.k, args.m, args.canonical, args.queries, wd, args.keep)))
+    print(json.dumps(run(args.strings, args.length, args.k, args.m, args.canonical, args.queries, wd, args.keep, args.index)))
 
 
 if __name__ == "__main__":
