@@ -143,6 +143,13 @@ SSHASH_GPU_API int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const
 SSHASH_GPU_API int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n,
                             uint64_t* kmers_out, void* stream);
 
+/* Batched dictionary::weight(kmer_id) (include/dictionary.hpp:65-66, src/dictionary.cpp:96-100,
+   include/weights.hpp:148-153): the abundance stored for each k-mer id of a weighted dictionary
+   (built with --weighted).  Ids must be < num_kmers.  SSHASH_GPU_EINVAL if the dictionary is not
+   weighted (the reference asserts). */
+SSHASH_GPU_API int sshash_gpu_weight_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n,
+                            uint64_t* weights_out, void* stream);
+
 /*
  * Navigational queries (include/dictionary.hpp:50-66, src/dictionary.cpp:112-201).  For each of the
  * n inputs 8 results are produced: forward[A,C,T,G] then backward[A,C,T,G] (neighbourhood<Kmer>,

@@ -34,6 +34,8 @@ def lib():
         l.oracle_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         l.oracle_lookup_batch_ascii.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         l.oracle_access_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        l.oracle_weight_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        l.oracle_weighted.argtypes = [C.c_void_p]
         l.oracle_kmer_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         l.oracle_string_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         l.oracle_streaming_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
@@ -90,6 +92,15 @@ class OracleDictionary:
         out = np.empty(ids.size * self.words, dtype=np.uint64)
         lib().oracle_access_batch(self.h, ids.ctypes.data, ids.size, out.ctypes.data)
         return out if self.words == 1 else out.reshape(-1, 2)
+
+    def weighted(self) -> bool:
+        return bool(lib().oracle_weighted(self.h))
+
+    def weight(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.empty(ids.size, dtype=np.uint64)
+        lib().oracle_weight_batch(self.h, ids.ctypes.data, ids.size, out.ctypes.data)
+        return out
 
     def kmer_neighbours(self, kmers, check_rc: bool = True, which: int = 3):
         a = np.ascontiguousarray(kmers, dtype=np.uint64)

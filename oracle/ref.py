@@ -69,13 +69,14 @@ def _lib(max_k: int):
         lib.ref_close.argtypes = [C.c_void_p]
         lib.ref_info.argtypes = [C.c_void_p, C.POINTER(Info)]
         lib.ref_build.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64,
-                                  C.c_char_p, C.c_char_p, C.c_int]
+                                  C.c_char_p, C.c_char_p, C.c_int, C.c_int]
         lib.ref_lookup_batch.restype = C.c_double
         lib.ref_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_uint64]
         lib.ref_lookup_batch_ascii.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p,
                                                C.c_void_p]
         lib.ref_access_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.ref_weight_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.ref_kmer_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         lib.ref_string_neighbours_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.ref_streaming_file.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(Report),
@@ -88,13 +89,14 @@ def _lib(max_k: int):
 
 
 def build(input_path: str, k: int, m: int, output: str, canonical: bool = False, threads: int = 1,
-          seed: int = 0, tmp_dir: str = "", max_k: int | None = None, verbose: bool = False) -> None:
-    """sshash build -i input -k k -m m [--canonical] -o output (tools/build.cpp)."""
+          seed: int = 0, tmp_dir: str = "", max_k: int | None = None, verbose: bool = False,
+          weighted: bool = False) -> None:
+    """sshash build -i input -k k -m m [--canonical] [--weighted] -o output (tools/build.cpp)."""
     if max_k is None:
         max_k = 31 if k <= 31 else 63
     lib = _lib(max_k)
     rc = lib.ref_build(input_path.encode(), k, m, int(canonical), threads, seed, tmp_dir.encode(),
-                       output.encode(), int(verbose))
+                       output.encode(), int(verbose), int(weighted))
     if rc != 0:
         raise RuntimeError("reference build failed: " + lib.ref_last_error().decode())
 
@@ -153,6 +155,13 @@ class RefDictionary:
         out = np.empty(ids.size * self.words, dtype=np.uint64)
         self.lib.ref_access_batch(self.h, ids.ctypes.data, ids.size, out.ctypes.data)
         return out if self.words == 1 else out.reshape(-1, 2)
+
+    def weight(self, ids):
+        """dictionary::weight(kmer_id) (src/dictionary.cpp:96-100)"""
+        a = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.empty(a.size, dtype=np.uint64)
+        self.lib.ref_weight_batch(self.h, a.ctypes.data, a.size, out.ctypes.data)
+        return out
 
     def kmer_neighbours(self, kmers, check_rc: bool = True, which: int = 3):
         """(n, 8) lookup_result records: forward[A,C,T,G], backward[A,C,T,G]."""

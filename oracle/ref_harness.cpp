@@ -14,6 +14,7 @@
  *   ref_info             k(), m(), canonical(), num_kmers(), ... (include/dictionary.hpp:31-38)
  *   ref_lookup_batch     dictionary::lookup(Kmer, check_rc)      (src/dictionary.cpp:64-78)
  *   ref_access_batch     dictionary::access                      (src/dictionary.cpp:90-94)
+ *   ref_weight_batch     dictionary::weight                      (src/dictionary.cpp:96-100)
  *   ref_kmer_neighbours_batch / ref_string_neighbours_batch
  *                        dictionary::kmer_neighbours etc.        (src/dictionary.cpp:112-201)
  *   ref_streaming_file   dictionary::streaming_query_from_file   (src/query.cpp:118-175)
@@ -63,7 +64,7 @@ const char* ref_last_error() { return g_err.c_str(); }
 int ref_max_k() { return default_kmer_t::max_k; }
 
 int ref_build(const char* input, uint64_t k, uint64_t m, int canonical, uint64_t threads,
-              uint64_t seed, const char* tmp_dir, const char* output, int verbose) {
+              uint64_t seed, const char* tmp_dir, const char* output, int verbose, int weighted) {
     try {
         build_configuration cfg;
         cfg.k = k;
@@ -72,6 +73,7 @@ int ref_build(const char* input, uint64_t k, uint64_t m, int canonical, uint64_t
         cfg.num_threads = threads ? threads : 1;
         if (seed) cfg.seed = seed;
         cfg.verbose = verbose != 0;
+        cfg.weighted = weighted != 0;       // tools/build.cpp:63
         if (tmp_dir && *tmp_dir) {
             cfg.tmp_dirname = tmp_dir;
             essentials::create_directory(cfg.tmp_dirname);
@@ -194,6 +196,11 @@ void ref_access_batch(void* h, const uint64_t* ids, uint64_t n, uint64_t* kmers_
 
 /* which: 1 = kmer_forward_neighbours, 2 = kmer_backward_neighbours, 3 = kmer_neighbours.
    out: 8 records per k-mer: forward[A,C,T,G] then backward[A,C,T,G] (include/util.hpp:77-81). */
+void ref_weight_batch(void* h, const uint64_t* ids, uint64_t n, uint64_t* weights_out) {
+    auto* d = static_cast<dictionary_type*>(h);
+    for (uint64_t i = 0; i != n; ++i) weights_out[i] = d->weight(ids[i]);
+}
+
 void ref_kmer_neighbours_batch(void* h, const uint64_t* kmers, uint64_t n, int check_rc, int which,
                                ref_lookup_result* out) {
     auto* d = static_cast<dictionary_type*>(h);

@@ -63,7 +63,9 @@ typedef struct {
     cvec_t mid_load;
     /* skew_index, sparse_and_skew_index.hpp:60-76 */
     uint64_t n_ski; pphf_t* ski_mphfs; uint64_t n_pos; cvec_t* positions; cvec_t heavy;
-    uint64_t weights_bytes; /* skipped, weights.hpp:182-187 */
+    uint64_t weights_bytes;
+    /* weights.hpp:182-187 */
+    cvec_t w_values; ef_t w_lengths; cvec_t w_dict;
     int kmer_bits;          /* 64 or 128: which reference build wrote the file */
     uint8_t* file; uint64_t file_size;
 } oracle_dict;
@@ -139,6 +141,8 @@ void oracle_close(oracle_dict* d) {
     free(d->ski_mphfs);
     for (uint64_t i = 0; i != d->n_pos; ++i) free_cvec(&d->positions[i]);
     free(d->positions); free_cvec(&d->heavy);
+    free_cvec(&d->w_values); free(d->w_lengths.high.data); free_darray(&d->w_lengths.d1); free_darray(&d->w_lengths.d0);
+    free_cvec(&d->w_lengths.low); free_cvec(&d->w_dict);
     free(d);
 }
 
@@ -178,6 +182,7 @@ oracle_dict* oracle_open(const char* path, int max_k, char* err, uint64_t errlen
     for (uint64_t i = 0; i != d->n_pos; ++i) rd_cvec(&r, &d->positions[i]);
     rd_cvec(&r, &d->heavy);
     d->weights_bytes = (uint64_t)(r.end - r.p);
+    rd_cvec(&r, &d->w_values); rd_ef(&r, &d->w_lengths); rd_cvec(&r, &d->w_dict);     /* weights.hpp:182-187 */
     d->file_size = sz;
     free(buf);
     if (r.fail || k2 != d->k || m2 != d->m) { snprintf(err, errlen, "malformed index file"); oracle_close(d); return NULL; }
@@ -578,6 +583,33 @@ void oracle_access_batch(const oracle_dict* d, const uint64_t* ids, uint64_t n, 
         u128 x = read_kmer_at(d, d->k, 2 * offset);
         if (d->kmer_bits == 64) kmers_out[q] = (uint64_t)x;
         else { kmers_out[2 * q] = (uint64_t)x; kmers_out[2 * q + 1] = (uint64_t)(x >> 64); }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Weights: dictionary::weight dictionary.cpp:96-100 -> weights::weight weights.hpp:148-153:
+ *   i = interval_lengths.prev_leq(kmer_id).pos; weight = dictionary[ interval_values[i] ]
+ * elias_fano::prev_leq (elias_fano.hpp:236-258) = the rightmost element <= x, saturating to the last
+ * one for x >= back(); restated as a binary search over elias_fano::access (:181-185) instead of
+ * the reference's select0 + forward scan (:385-430) -- same answer for a sorted sequence.
+ * ---------------------------------------------------------------------------------------- */
+static uint64_t ef_prev_leq_pos(const ef_t* e, uint64_t x) {
+    uint64_t n = e->low.size;
+    if (x >= e->back) return n - 1;
+    if (ef_access(e, 0) > x) return ~0ull;
+    uint64_t lo = 0, hi = n - 1;                 /* access(lo) <= x < access(hi) */
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (ef_access(e, mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+int oracle_weighted(const oracle_dict* d) { return d->w_dict.size != 0; }   /* weights::empty, weights.hpp:146 */
+void oracle_weight_batch(const oracle_dict* d, const uint64_t* ids, uint64_t n, uint64_t* weights_out) {
+    for (uint64_t q = 0; q != n; ++q) {
+        uint64_t i = ef_prev_leq_pos(&d->w_lengths, ids[q]);
+        uint64_t id = cvec_access(&d->w_values, i);
+        weights_out[q] = cvec_access(&d->w_dict, id);
     }
 }
 

@@ -252,13 +252,42 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     ix.n_ends = ends.size();
     ends.push_back(~0ull); ends.push_back(~0ull);   // scan sentinels
 
+    // weights (include/weights.hpp:182-187): interval starts decoded from their Elias-Fano sequence +
+    // a sampled directory; both tables go into the hot slab, the two compact vectors are verbatim
+    std::vector<uint64_t> wstarts;
+    std::vector<uint32_t> wdir;
+    ix.n_weight_intervals = 0;
+    ix.weight_dir_shift = 0;
+    if (f.weighted) {
+        const uint64_t nw = f.weight_interval_values.size;
+        f.decode_elias_fano(f.weight_interval_lengths, nw + 1, wstarts);
+        if (wstarts.size() != nw + 1 || wstarts[0] != 0 || wstarts.back() != f.num_kmers || (nw >> 32))
+            return fail(SSHASH_GPU_EFORMAT, "malformed index file (weight intervals)");
+        for (uint64_t i = 1; i <= nw; ++i)
+            if (wstarts[i] <= wstarts[i - 1]) return fail(SSHASH_GPU_EFORMAT, "malformed index file (weight intervals not increasing)");
+        uint32_t shift = 0;
+        while ((f.num_kmers >> shift) > 2 * nw + 64) ++shift;
+        wdir.resize((f.num_kmers >> shift) + 3);
+        uint64_t j = 0;
+        for (uint64_t h = 0; h != wdir.size(); ++h) {      // index of the last start <= (h << shift), interval starts only
+            const uint64_t lim = h << shift;
+            while (j + 1 < nw && wstarts[j + 1] <= lim) ++j;
+            wdir[h] = (uint32_t)j;
+        }
+        ix.n_weight_intervals = nw;
+        ix.weight_dir_shift = shift;
+        ix.weight_values = up.compact(f, f.weight_interval_values);
+        ix.weight_dict = up.compact(f, f.weight_dictionary);
+    }
+
     // HOT SLAB: the arrays every lookup touches (pilots, free slots, partition table, end-points and
     // their directory) live in ONE allocation so that a single L2 access-policy window can keep
     // them persistent in L2 while the cold, much larger arrays (codewords, strings) stream through.
     struct Piece { const void* src; uint64_t bytes; uint64_t off; };
-    Piece pieces[5] = {{pilots_host.data(), pilots_host.size() * 8, 0}, {free_pool.data(), free_pool.size() * 4, 0},
+    Piece pieces[7] = {{pilots_host.data(), pilots_host.size() * 8, 0}, {free_pool.data(), free_pool.size() * 4, 0},
                        {parts.data(), parts.size() * sizeof(DevPhfPart), 0}, {ends.data(), ends.size() * 8, 0},
-                       {dir.data(), dir.size() * 4, 0}};
+                       {dir.data(), dir.size() * 4, 0}, {wstarts.data(), wstarts.size() * 8, 0},
+                       {wdir.data(), wdir.size() * 4, 0}};
     uint64_t slab_bytes = 0;
     for (auto& p : pieces) { p.off = slab_bytes; slab_bytes += (p.bytes + kPadBytes + 255) & ~255ull; }
     uint8_t* slab = nullptr;
@@ -275,6 +304,8 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     const DevPhfPart* d_parts = reinterpret_cast<const DevPhfPart*>(slab + pieces[2].off);
     ix.ends = reinterpret_cast<const uint64_t*>(slab + pieces[3].off);
     ix.ends_dir = reinterpret_cast<const uint32_t*>(slab + pieces[4].off);
+    ix.weight_starts = reinterpret_cast<const uint64_t*>(slab + pieces[5].off);
+    ix.weight_dir = reinterpret_cast<const uint32_t*>(slab + pieces[6].off);
     ix.mphf.parts = d_parts + ix.mphf.first_part_;
     for (uint32_t i = 0; i != ix.n_skew; ++i) ix.skew[i].parts = d_parts + ix.skew[i].first_part_;
     d->ctx.hot_base = slab;
@@ -532,6 +563,21 @@ int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_id
                        });
 }
 
+int sshash_gpu_weight_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n, uint64_t* weights_out,
+                            void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (!dict->ix.n_weight_intervals) return fail(SSHASH_GPU_EINVAL, "the dictionary is not weighted");
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!kmer_ids || !weights_out) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const DeviceIndex& ix = dict->ix;
+    const LaunchCtx& sms = dict->ctx;
+    return run_batched(dict, kmer_ids, 8, weights_out, 8, n, stream,
+                       [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                           return launch_weight(ix, sms, static_cast<const uint64_t*>(in), cn, static_cast<uint64_t*>(out), s);
+                       });
+}
+
 // kmer_neighbours / string_neighbours: n inputs -> 8n results (forward A,C,T,G then backward A,C,T,G)
 static int neighbours_common(const sshash_gpu_dict* dict, const uint64_t* in, bool strings, uint64_t n, int check_rc, int which,
                              uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
@@ -605,8 +651,7 @@ static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const cha
     if (use_anchors) CU(ensure(w.d_anchors, w.anchors_cap, streaming_anchor_bytes(num_reads)));
     CU(launch_window_offsets(ix.k, d_read_offsets, num_reads, w.d_win_offsets, w.d_block_sums, s));
     CU(launch_streaming(ix, dict->ctx, d_bases, d_read_offsets, w.d_win_offsets, num_reads, use_anchors ? w.d_anchors : nullptr,
-                        w.d_win_id, w.d_win_aux,
-                        d_ids_out, w.d_counters, s));
+                        w.d_win_id, w.d_win_aux, d_ids_out, max_windows, w.d_counters, s));
     return SSHASH_GPU_OK;
 }
 
@@ -697,7 +742,7 @@ int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char
         std::fprintf(stderr, "unsupported query file format\n");
         return SSHASH_GPU_OK;
     }
-    if (multiline && !fastq) return fail(SSHASH_GPU_EINVAL, "multiline FASTA is not supported by the GPU streaming driver");
+    if (multiline && fastq) multiline = 0;   // query.cpp:154-163: the flag only affects FASTA input
     gzFile gz = gzopen(filename, "rb");   // transparently reads uncompressed files too
     if (!gz) return fail(SSHASH_GPU_EIO, "error in opening the file '" + fn + "'");
     gzbuffer(gz, 1 << 20);
@@ -728,6 +773,24 @@ int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char
         bases.clear(); offsets.assign(1, 0);
         return SSHASH_GPU_OK;
     };
+    if (multiline) {
+        // streaming_query_from_fasta_file_multiline (query.cpp:9-51) + buffered_lines_iterator
+        // (util.hpp:287-340): the reference concatenates ALL lines -- header lines included, their
+        // characters simply make windows invalid -- and slides over the concatenation without
+        // resetting the query; only an EMPTY line ends the run (buffer cleared, query.reset()).  The
+        // 1024-character refills keep the last k-1 characters, so every window of a run is visited
+        // exactly once: a run is one read.  (A run shorter than k-1 characters underflows num_kmers
+        // in the reference, :22; here it contributes nothing.)
+        for (;;) {
+            const size_t before = bases.size();
+            if (!getline(&bases)) break;
+            if (bases.size() == before) {            // empty line: end of the run
+                if (bases.size() > offsets.back()) offsets.push_back(bases.size());
+                if (bases.size() >= (256u << 20)) { st = flush(); if (st) { gzclose(gz); return st; } }
+            }
+        }
+        if (bases.size() > offsets.back()) offsets.push_back(bases.size());
+    } else
     for (;;) {
         if (!getline(nullptr)) break;                 // header
         if (!getline(&bases)) { /* header without sequence: empty read */ }

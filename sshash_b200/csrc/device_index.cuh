@@ -21,6 +21,9 @@
 //   ends_dir       u32[]  ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none):
 //                         replaces hints_0 + the unary scan of high_bits with one 4-byte load + a
 //                         short linear scan of `ends`
+//   weight_starts  u64[]  (weighted indexes) first k-mer id of every weight interval, DECODED from
+//                         the Elias-Fano weights::m_weight_interval_lengths (+ a sampled directory
+//                         weight_dir like ends_dir); weight_values / weight_dict: verbatim
 // Everything else (k, m, seeds, widths, begin_buckets_of_size[65]) travels in the kernel
 // parameter block (`DeviceIndex`, < 1 KB, constant-cached).
 //
@@ -82,6 +85,13 @@ struct DeviceIndex {
     const uint64_t* ends;
     uint64_t n_ends;
     const uint32_t* ends_dir;
+    // weights (include/weights.hpp:148-153,182-187); n_weight_intervals == 0 <=> not weighted
+    const uint64_t* weight_starts;     // n_weight_intervals + 1 entries (+ sentinels)
+    const uint32_t* weight_dir;        // weight_dir[h] = index of the last start <= (h << weight_dir_shift)
+    uint64_t n_weight_intervals;
+    DevCompact weight_values;          // m_weight_interval_values: interval -> id in the dictionary
+    DevCompact weight_dict;            // m_weight_dictionary: id -> weight
+    uint32_t weight_dir_shift;
     uint32_t begin_buckets_of_size[65];
     uint32_t cw_code_bits;     // width of the reference's codeword inside a `codewords` entry
     uint32_t cw_fp_bits;       // fingerprint bits above it (0 = verbatim vector)

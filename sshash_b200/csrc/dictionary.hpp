@@ -9,6 +9,7 @@
 //   lookup_result lookup(Kmer, bool = true)               lookup(kmer_t)  (dictionary.hpp:42, dictionary.cpp:64-78)
 //   bool is_member(char const* / Kmer, bool = true)       same            (dictionary.hpp:75-76)
 //   void access(uint64_t kmer_id, char* string_kmer)      same            (dictionary.hpp:71)
+//   uint64_t weight(uint64_t kmer_id)                     same            (dictionary.hpp:65-66, weights.hpp:148-153)
 //   kmer_neighbours / kmer_forward_neighbours /           same            (dictionary.hpp:50-66, dictionary.cpp:112-201)
 //     kmer_backward_neighbours / string_neighbours
 //   streaming_query_from_file(filename, multiline)        same            (dictionary.hpp:81-82)
@@ -103,6 +104,12 @@ public:
         uint_kmer_to_string(kmer_t{w[0], w[1]}, string_kmer, k());
     }
 
+    uint64_t weight(uint64_t kmer_id) const {
+        uint64_t w = 0;
+        check(sshash_gpu_weight_batch(m_dict, &kmer_id, 1, &w, nullptr));
+        return w;
+    }
+
     /* Batched forms: host or device pointers; `stream` only matters for device pointers. */
     void lookup_batch(uint64_t const* kmers, uint64_t n, uint64_t* kmer_ids, bool check_reverse_complement = true,
                       lookup_result* full = nullptr, void* stream = nullptr) const {
@@ -118,6 +125,10 @@ public:
     }
     void access_batch(uint64_t const* kmer_ids, uint64_t n, uint64_t* kmers_out, void* stream = nullptr) const {
         check(sshash_gpu_access_batch(m_dict, kmer_ids, n, kmers_out, stream));
+    }
+
+    void weight_batch(uint64_t const* kmer_ids, uint64_t n, uint64_t* weights_out, void* stream = nullptr) const {
+        check(sshash_gpu_weight_batch(m_dict, kmer_ids, n, weights_out, stream));
     }
 
     /* Navigational queries (include/dictionary.hpp:50-66): forward[A,C,T,G] then backward[A,C,T,G]. */

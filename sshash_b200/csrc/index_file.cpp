@@ -152,8 +152,14 @@ std::string IndexFile::open(const char* path, int* status_out) {
     weights_bytes = file_bytes - r.pos;
     {   // weights: compact_vector interval_values first (weights.hpp:182-187); non-empty <=> weighted
         Reader w{base, file_bytes, r.pos};
-        uint64_t n = w.pod<uint64_t>();
-        weighted = !w.fail && n != 0;
+        weight_interval_values = w.compact_vector();
+        weight_interval_lengths = w.elias_fano();
+        weight_dictionary = w.compact_vector();
+        weighted = !w.fail && weight_interval_values.size != 0;
+        if (weighted && (weight_interval_lengths.low_bits.size != weight_interval_values.size + 1 ||
+                         weight_dictionary.size == 0 || weight_interval_values.width > 57 ||
+                         weight_dictionary.width > 57))
+            return err(SSHASH_GPU_EFORMAT, "malformed index file (weights)");
     }
     if (k2 != k || m2 != m || k == 0 || m == 0 || m > k || k > 63 || m > 31)
         return err(SSHASH_GPU_EFORMAT, "malformed index file (k/m)");
@@ -166,9 +172,11 @@ std::string IndexFile::open(const char* path, int* status_out) {
     return "";
 }
 
-void IndexFile::decode_elias_fano(const EliasFanoView& ef, uint64_t n, std::vector<uint32_t>& out) const {
-    const uint8_t* high = ptr(ef.high_bits.data);
-    const uint8_t* low = ptr(ef.low_bits.data);
+namespace {
+template <typename T>
+void decode_ef(const IndexFile& f, const EliasFanoView& ef, uint64_t n, std::vector<T>& out) {
+    const uint8_t* high = f.ptr(ef.high_bits.data);
+    const uint8_t* low = f.ptr(ef.low_bits.data);
     const uint64_t l = ef.low_bits.width, lmask = ef.low_bits.mask;
     const uint64_t nwords = ef.high_bits.data.n;
     uint64_t i = 0;
@@ -184,10 +192,18 @@ void IndexFile::decode_elias_fano(const EliasFanoView& ef, uint64_t n, std::vect
                 if (sh + l > 64) lo |= load_word(low, wi + 1) << (64 - sh);
                 lo &= lmask;
             }
-            out.push_back(static_cast<uint32_t>(((pos - i) << l) | lo));
+            out.push_back(static_cast<T>(((pos - i) << l) | lo));
             ++i;
         }
     }
+}
+}  // namespace
+
+void IndexFile::decode_elias_fano(const EliasFanoView& ef, uint64_t n, std::vector<uint32_t>& out) const {
+    decode_ef(*this, ef, n, out);
+}
+void IndexFile::decode_elias_fano(const EliasFanoView& ef, uint64_t n, std::vector<uint64_t>& out) const {
+    decode_ef(*this, ef, n, out);
 }
 
 void IndexFile::decode_endpoints(std::vector<uint64_t>& out) const {

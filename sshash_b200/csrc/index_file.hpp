@@ -72,8 +72,12 @@ struct IndexFile {
     std::vector<PartitionedPhfView> skew_mphfs;      // skew_index, :60-76
     std::vector<CompactVectorView> skew_positions;
     CompactVectorView heavy_load_buckets;
-    uint64_t weights_off = 0, weights_bytes = 0;     // weights.hpp:182-187: skipped, not parsed
+    uint64_t weights_off = 0, weights_bytes = 0;
     bool weighted = false;
+    // weights.hpp:182-187 (populated iff weighted)
+    CompactVectorView weight_interval_values;
+    EliasFanoView weight_interval_lengths;           // elias_fano<true,false>: same byte layout
+    CompactVectorView weight_dictionary;
 
     // mapping
     const uint8_t* base = nullptr;
@@ -94,6 +98,7 @@ struct IndexFile {
     // Elias-Fano i-th value = ((position of the i-th set bit of high_bits - i) << l) | low[i]
     // (elias_fano.hpp:181-185); walking the set bits in order needs no select structure.
     void decode_elias_fano(const EliasFanoView& ef, uint64_t n, std::vector<uint32_t>& out) const;
+    void decode_elias_fano(const EliasFanoView& ef, uint64_t n, std::vector<uint64_t>& out) const;
     // end-points: same with l = 8 and byte-wide low parts (endpoints_sequence.hpp:160-163)
     void decode_endpoints(std::vector<uint64_t>& out) const;
 };

@@ -267,6 +267,30 @@ access_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// batched dictionary::weight (src/dictionary.cpp:96-100 -> weights::weight, include/weights.hpp:148-153):
+// interval = prev_leq(kmer_id) over the interval starts (elias_fano.hpp:254-258; the starts are
+// strictly increasing, so it is the last start <= id), then two compact-vector reads.  The sampled
+// directory narrows the binary search to the intervals that begin inside one 2^shift block of ids.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+weight_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ ids, uint64_t n,
+              uint64_t* __restrict__ weights_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t id = __ldcs(ids + i);
+        if (id >= ix.num_kmers) id = ix.num_kmers - 1;   // the reference's prev_leq saturates (:252); ids must be < num_kmers
+        const uint64_t h = id >> ix.weight_dir_shift;
+        uint64_t lo = ld32<true>(ix.weight_dir + h), hi = ld32<true>(ix.weight_dir + h + 1);
+        while (lo < hi) {                                // last start <= id inside [lo, hi]
+            const uint64_t mid = lo + (hi - lo + 1) / 2;
+            if (ld64<true>(ix.weight_starts + mid) <= id) lo = mid; else hi = mid - 1;
+        }
+        const uint64_t wid = compact_get<true>(ix.weight_values, lo);
+        __stcs(weights_out + i, compact_get<true>(ix.weight_dict, wid));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // streaming membership, step 1: one lookup per window.  The reference defines every streamed
 // result as equal to dict->lookup(kmer) (include/streaming_query.hpp:107), which is what makes the
 // windows independent.  One WARP per read, one lane per window, 32 windows (a "tile") at a time;
@@ -281,7 +305,8 @@ access_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict
 //     leftmost of the reversed order -- include/util.hpp:262-283 on kmer and on kmer_rc).
 //   * on a regular index, windows that miss the forward pass are parked in a per-warp queue and
 //     their reverse-complement pass runs on full groups of 32 lanes (as in lookup_kernel).
-// Window record: id (u64) + string_id (low 62 bits) | flags (bit 63: backward, bit 62: valid)
+// Window record: id (u64) + aux = string_id (low 59 bits) | flags: bit 63 backward, bit 62 valid,
+// bit 61 first window of its read, bit 60 / 59 the k-mer is the first / last one of its string
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool valid_base(uint8_t c) {  // canonicalize_basepair_forward_map, kmer.hpp:209-219
     uint8_t u = c & 0xDF;
@@ -315,10 +340,19 @@ template <> struct StreamQueue<2> {
     __device__ Kmer<2> get(uint32_t s) const { return {lo[s], hi[s]}; }
 };
 
+constexpr uint64_t kAuxBackward = 1ull << 63, kAuxValid = 1ull << 62, kAuxFirstOfRead = 1ull << 61,
+                   kAuxFirstInString = 1ull << 60, kAuxLastInString = 1ull << 59, kAuxSidMask = (1ull << 59) - 1;
+
 __device__ __forceinline__ void store_window(uint64_t* __restrict__ win_id, uint64_t* __restrict__ win_aux, uint64_t w,
-                                             const LookupResult& r, bool backward) {
+                                             const LookupResult& r, bool backward, bool first_of_read, uint32_t k) {
     win_id[w] = r.kmer_id;
-    win_aux[w] = (1ull << 62) | (r.string_id & ((1ull << 62) - 1)) | (backward ? (1ull << 63) : 0);
+    uint64_t aux = kAuxValid | (backward ? kAuxBackward : 0) | (first_of_read ? kAuxFirstOfRead : 0);
+    if (r.kmer_id != ~0ull) {
+        aux |= r.string_id & kAuxSidMask;
+        if (r.kmer_id_in_string == 0) aux |= kAuxFirstInString;
+        if (r.kmer_id_in_string + k == r.string_end - r.string_begin) aux |= kAuxLastInString;
+    }
+    win_aux[w] = aux;
 }
 
 template <int W>
@@ -492,14 +526,15 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                         if (kmer_eq(sk, back ? xr : x)) {
                             resolved = true;
                             win_id[w0 + w] = (uint64_t)oj - sid * (k - 1);
-                            win_aux[w0 + w] = (1ull << 62) | sid | (back ? (1ull << 63) : 0);
+                            win_aux[w0 + w] = kAuxValid | sid | (back ? kAuxBackward : 0) | (w == 0 ? kAuxFirstOfRead : 0) |
+                                              (oj == a[1] ? kAuxFirstInString : 0) | (oj + (int64_t)k == a[2] ? kAuxLastInString : 0);
                         }
                     }
                 }
-                if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = 0; }
+                if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = w == 0 ? kAuxFirstOfRead : 0; }
                 valid = valid && !resolved;              // from here on: windows that still need a lookup
                 if (__ballot_sync(0xffffffffu, valid) == 0) continue;
-            } else if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = 0; }
+            } else if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = w == 0 ? kAuxFirstOfRead : 0; }
             // ---- m-mer hashes of the tile, both strands (mixer_64::hash, hash_util.hpp:91) -------------
             __syncwarp();
 #pragma unroll
@@ -540,16 +575,16 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                         found = lookup_canonical_with<W, false>(ix, x, xr, mf, res);
                         if (!found) found = lookup_canonical_with<W, false>(ix, x, xr, mr, res);
                     }
-                    store_window(win_id, win_aux, w0 + w, res, found && res.kmer_orientation < 0);
+                    store_window(win_id, win_aux, w0 + w, res, found && res.kmer_orientation < 0, w == 0, k);
                 } else if (lookup_regular_with<W, false>(ix, x, mf, res)) {
-                    store_window(win_id, win_aux, w0 + w, res, false);
+                    store_window(win_id, win_aux, w0 + w, res, false, w == 0, k);
                 } else {
                     park = true;
                 }
             }
             if (canonical) continue;
             const uint32_t mask = __ballot_sync(0xffffffffu, park);
-            if (park) q.put(queued + __popc(mask & ((1u << lane) - 1)), xr, mr, w0 + w);
+            if (park) q.put(queued + __popc(mask & ((1u << lane) - 1)), xr, mr, (w0 + w) | (w == 0 ? kAuxFirstOfRead : 0));
             queued += __popc(mask);
             __syncwarp();
             if (queued >= 32) {
@@ -557,7 +592,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                 const uint32_t e = queued + lane;
                 LookupResult res;
                 const bool found = lookup_regular_with<W, false>(ix, q.get(e), Minimizer{q.mini[e], q.pos[e]}, res);
-                store_window(win_id, win_aux, q.widx[e], res, found);
+                store_window(win_id, win_aux, q.widx[e] & ~kAuxFirstOfRead, res, found, (q.widx[e] & kAuxFirstOfRead) != 0, k);
                 __syncwarp();
             }
         }
@@ -566,7 +601,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
     if (!canonical && lane < queued) {
         LookupResult res;
         const bool found = lookup_regular_with<W, false>(ix, q.get(lane), Minimizer{q.mini[lane], q.pos[lane]}, res);
-        store_window(win_id, win_aux, q.widx[lane], res, found);
+        store_window(win_id, win_aux, q.widx[lane] & ~kAuxFirstOfRead, res, found, (q.widx[lane] & kAuxFirstOfRead) != 0, k);
     }
 }
 
@@ -582,22 +617,6 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
 // (almost) never match and are counted as searches, exactly as the reference does.
 // ------------------------------------------------------------------------------------------------
 template <int W> struct KmerIter;
-template <> struct KmerIter<1> {
-    uint64_t pos, avail, buff;
-    __device__ void at(uint64_t p) { pos = p; avail = 0; buff = 0; }
-    __device__ uint64_t word(const DeviceIndex& ix, uint64_t p) const { return read_word64(ix.strings, p); }
-    __device__ void fill(const DeviceIndex& ix) { buff = word(ix, pos); avail = 64; }
-    __device__ void fill_reverse(const DeviceIndex& ix) {
-        buff = word(ix, (pos > 64 ? pos : 64) - 64);
-        avail = pos < 64 ? pos : 64;
-        uint64_t pad = 64 - avail;
-        buff = pad >= 64 ? 0 : buff << pad;
-    }
-    __device__ Kmer<1> get(const DeviceIndex& ix) { if (avail < 2 * ix.k) fill(ix); return {buff & low_mask(2 * ix.k)}; }
-    __device__ Kmer<1> get_reverse(const DeviceIndex& ix) { if (avail < 2 * ix.k) fill_reverse(ix); return {buff >> (64 - 2 * ix.k)}; }
-    __device__ void next(const DeviceIndex& ix) { if (avail < 2) fill(ix); buff >>= 2; avail -= 2; pos += 2; }
-    __device__ void next_reverse(const DeviceIndex& ix) { if (avail < 2) fill_reverse(ix); buff <<= 2; avail -= 2; pos -= 2; }
-};
 template <> struct KmerIter<2> {
     uint64_t pos, avail, lo, hi;  // buff = hi:lo
     __device__ void at(uint64_t p) { pos = p; avail = 0; lo = hi = 0; }
@@ -634,18 +653,6 @@ template <> struct KmerIter<2> {
 };
 
 template <int W> struct RollingKmer;
-template <> struct RollingKmer<1> {
-    Kmer<1> x, xr;
-    __device__ void init(const char* s, uint32_t k) {      // first k-1 characters; push() adds the k-th
-        x.lo = 0; xr.lo = 0;
-        for (uint32_t i = 0; i + 1 < k; ++i) push((uint8_t)s[i], k);
-    }
-    __device__ void push(uint8_t c, uint32_t k) {
-        const uint64_t code = (c >> 1) & 3;
-        x.lo = (x.lo >> 2) | (code << (2 * (k - 1)));
-        xr.lo = ((xr.lo << 2) | (code ^ 2)) & low_mask(2 * k);
-    }
-};
 template <> struct RollingKmer<2> {
     Kmer<2> x, xr;
     __device__ void init(const char* s, uint32_t k) {
@@ -712,7 +719,7 @@ stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restric
                 else {
                     n_search += 1;
                     backward = (aux >> 63) != 0;
-                    const uint64_t sid = aux & ((1ull << 62) - 1);
+                    const uint64_t sid = aux & kAuxSidMask;
                     const uint64_t sb = ld64<true>(ix.ends + sid), se = ld64<true>(ix.ends + sid + 1);
                     const uint64_t ko = cur_id + sid * (k - 1);          // kmer_offset in bases
                     const uint64_t in_string = ko - sb;
@@ -740,6 +747,55 @@ stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restric
     if (threadIdx.x < 5 && sh[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sh[threadIdx.x]);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// streaming membership, step 2 for 64-bit k-mers: the same counters WITHOUT the sequential replay.
+// With the 64-bit kmer_iterator the string k-mer the reference compares against (:88-99) is exactly
+// the next k-mer of the string in the previous window's direction, and the index holds every k-mer
+// once, so
+//     window i is an EXTENSION  <=>  windows i-1 and i are positive, window i-1's k-mer is not the
+//     last (forward) / first (backward) k-mer of its string (remaining > 0, :189-195), and
+//     id(i) == id(i-1) + orientation(i-1);
+// every other positive window is a SEARCH.  The state the reference carries (id, orientation,
+// remaining) is a function of window i-1's lookup result alone (:107 asserts streamed == looked-up),
+// so windows are classified independently, one thread each; the streamed ids ARE the window ids.
+// (The 128-bit build keeps stream_scan_kernel: its fill_buff_reverse word-order quirk makes the
+// outcome depend on the iterator's history.)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+stream_classify_kernel(const uint64_t* __restrict__ win_offsets, uint64_t num_reads, const uint64_t* __restrict__ win_id,
+                       const uint64_t* __restrict__ win_aux, unsigned long long* __restrict__ counters) {
+    const uint64_t total = win_offsets[num_reads];
+    unsigned long long n_search = 0, n_ext = 0, n_neg = 0, n_inv = 0, n_kmers = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const uint64_t aux = win_aux[g], id = win_id[g];
+        n_kmers += 1;
+        if (!(aux & kAuxValid)) { n_inv += 1; continue; }
+        if (id == ~0ull) { n_neg += 1; continue; }
+        bool ext = false;
+        if (!(aux & kAuxFirstOfRead)) {
+            const uint64_t paux = win_aux[g - 1], pid = win_id[g - 1];
+            if ((paux & kAuxValid) && pid != ~0ull) {
+                ext = (paux & kAuxBackward) ? (!(paux & kAuxFirstInString) && id + 1 == pid)
+                                            : (!(paux & kAuxLastInString) && id == pid + 1);
+            }
+        }
+        if (ext) n_ext += 1; else n_search += 1;
+    }
+    __shared__ unsigned long long sh[5];
+    if (threadIdx.x < 5) sh[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long v[5] = {n_kmers, n_search, n_ext, n_neg, n_inv};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        unsigned long long x = v[j];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&sh[j], x);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && sh[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sh[threadIdx.x]);
+}
 
 // ------------------------------------------------------------------------------------------------
 // win_offsets = exclusive prefix sum of max(0, len_r - k + 1) over the reads (three small kernels:
@@ -879,6 +935,12 @@ cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
     return launch(access_kernel<2>, grid, stream, ctx, ix, ids, n, kmers_out);
 }
 
+cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* weights_out,
+                          cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    return launch(weight_kernel, grid_for(n, ctx.sm_count, 8), stream, ctx, ix, ids, n, weights_out);
+}
+
 cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* in, bool strings, uint64_t n,
                               bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
                               cudaStream_t stream) {
@@ -921,8 +983,10 @@ cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint
 
 cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
                              const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
-                             uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream) {
+                             uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream) {
     if (num_reads == 0) return cudaSuccess;
+    // 64-bit k-mers: streamed ids == window ids, so the window kernel writes the caller's buffer directly
+    if (ix.kmer_words == 1 && ids_out) win_id = ids_out;
     Anchor* an = static_cast<Anchor*>(anchors);
     if (an) {
         const int grid = grid_for(num_reads * kAnchorsPerRead, ctx.sm_count, 8);
@@ -944,12 +1008,13 @@ cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const 
                        (const Anchor*)an, win_id, win_aux, counters + 5);
         if (e != cudaSuccess) return e;
     }
-    {
-        const int grid = grid_for(num_reads, ctx.sm_count, 8);
-        if (ix.kmer_words == 1)
-            return launch(stream_scan_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
-        return launch(stream_scan_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads, win_id, win_aux, ids_out, counters);
+    if (ix.kmer_words == 1) {
+        // 64-bit k-mers: the windows kernel wrote the streamed ids straight into ids_out (see below)
+        return launch(stream_classify_kernel, grid_for(total_windows_bound, ctx.sm_count, 8), stream, ctx, win_offsets, num_reads,
+                      (const uint64_t*)win_id, (const uint64_t*)win_aux, counters);
     }
+    return launch(stream_scan_kernel<2>, grid_for(num_reads, ctx.sm_count, 8), stream, ctx, ix, bases, read_offsets, win_offsets,
+                  num_reads, win_id, win_aux, ids_out, counters);
 }
 
 }  // namespace sshash_b200

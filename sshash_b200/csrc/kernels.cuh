@@ -39,6 +39,10 @@ cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const
                               bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
                               cudaStream_t stream);
 
+// dictionary::weight for n k-mer ids (weighted indexes only)
+cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* weights_out,
+                          cudaStream_t stream);
+
 // open time: re-encode ix.codewords (verbatim) into `out` (zeroed, width + fp_bits per entry) with
 // a fingerprint of each slot's minimizer above the codeword
 cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
@@ -49,11 +53,13 @@ cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint
                                   uint64_t* block_sums, cudaStream_t stream);
 uint64_t window_offsets_scratch_words(uint64_t num_reads);
 
-// Streaming membership over a batch of reads: per-window lookups, then the per-read replay of the
-// reference state machine.  counters[5] += {num_kmers, searches, extensions, negative, invalid}.
+// Streaming membership over a batch of reads: per-window lookups, then the classification of the
+// windows into searches / extensions (one thread per window for 64-bit k-mers, the per-read replay
+// of the reference state machine for 128-bit ones).  total_windows_bound >= number of windows.
+// counters[5] += {num_kmers, searches, extensions, negative, invalid}.
 cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
                              const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
-                             uint64_t* ids_out, unsigned long long* counters, cudaStream_t stream);
+                             uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream);
 // scratch for the per-read alignment anchors (pass nullptr as `anchors` to look every window up)
 uint64_t streaming_anchor_bytes(uint64_t num_reads);
 

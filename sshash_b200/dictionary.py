@@ -184,6 +184,18 @@ class Dictionary:
         x = int(w[0]) | (int(w[1]) << 64 if self.words == 2 else 0)
         return uint_kmer_to_string(x, self.k())
 
+    # ---- weight, include/dictionary.hpp:65-66 ---------------------------------------------------
+    def weight_batch(self, kmer_ids, stream: int = 0):
+        """dictionary::weight for a batch of k-mer ids (weighted dictionaries only)."""
+        kmer_ids = self._prep_in(kmer_ids)
+        n = kmer_ids.numel() if _is_torch(kmer_ids) else kmer_ids.size
+        out = self._alloc_like(kmer_ids, n, np.uint64, (n,))
+        check(self._lib.sshash_gpu_weight_batch(self._h, _ptr(kmer_ids), n, _ptr(out), stream))
+        return out
+
+    def weight(self, kmer_id: int) -> int:
+        return int(self.weight_batch(np.array([kmer_id], dtype=np.uint64))[0])
+
     # ---- navigational queries, include/dictionary.hpp:50-66 ------------------------------------
     def kmer_neighbours_batch(self, kmers, check_reverse_complement: bool = True, which: int = 3, full: bool = True):
         """Batched kmer_neighbours (which=3), kmer_forward_neighbours (1), kmer_backward_neighbours (2):

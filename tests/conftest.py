@@ -22,6 +22,7 @@ def load_manifest():
 
 MANIFEST = load_manifest()
 FIXTURES = sorted(MANIFEST)
+WEIGHTED = [n for n in FIXTURES if MANIFEST[n].get("weighted")]
 
 
 @pytest.fixture(scope="session")

@@ -26,7 +26,7 @@ from oracle import ref  # noqa: E402
 DATA = "/root/reference/data/unitigs_stitched/"
 TMP = "/tmp/sshash_golden_tmp"
 
-# name, source, k, m, canonical, nseq (None = whole file), build lib (31/63)
+# name, source, k, m, canonical, nseq (None = whole file), build lib (31/63) [, weighted]
 FIXTURES = [
     ("se_k31_m13", "salmonella_enterica_k31_ust.fa.gz", 31, 13, False, None, 31),   # BASELINE cfg 1/2
     ("sal100_k31_m7_reg", "salmonella_100_k31_ust.fa.gz", 31, 7, False, 3000, 31),  # heavy buckets, 2 skew partitions
@@ -37,6 +37,9 @@ FIXTURES = [
     ("se_k63_m7_reg", "se.ust.k63.fa.gz", 63, 7, False, 30, 63),                      # 128-bit + heavy (16-byte MPHF keys)
     ("se_k63_m8_canon", "se.ust.k63.fa.gz", 63, 8, True, 30, 63),                     # 128-bit canonical + heavy
     ("se_k47_m8", "se.ust.k47.fa.gz", 47, 8, False, 30, 63),                          # 32 < k < 63
+    # weighted dictionaries (README "--weighted"): abundances in the ab:Z: header field
+    ("sakai_k31_m13_weighted", "with_weights/ecoli_sakai.ust.k31.fa.gz", 31, 13, False, 400, 31, True),
+    ("ecoli_k31_m11_canon_weighted", "with_weights/ecoli.ust.k31.fa.gz", 31, 11, True, 60, 31, True),
 ]
 NQ = 12000  # positives per fixture (+ as many negatives)
 
@@ -159,15 +162,23 @@ def make_nav(name, lib):
 def main():
     os.makedirs(TMP, exist_ok=True)
     if "--nav-only" in sys.argv:
-        for name, _src, _k, _m, _canon, _nseq, lib in FIXTURES:
-            make_nav(name, lib)
+        for fx in FIXTURES:
+            make_nav(fx[0], fx[6])
         return
     manifest = {}
-    for name, src, k, m, canon, nseq, lib in FIXTURES:
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    if only:   # regenerate just these fixtures, keep the other manifest entries
+        with open(os.path.join(HERE, "manifest.json")) as f:
+            manifest = json.load(f)
+    for fx in FIXTURES:
+        name, src, k, m, canon, nseq, lib = fx[:7]
+        weighted = len(fx) > 7 and fx[7]
+        if only and name not in only:
+            continue
         fa = os.path.join(TMP, name + ".fa")
         subset(DATA + src, nseq, fa)
         idx = os.path.join(HERE, name + ".sshash")
-        ref.build(fa, k, m, idx, canonical=canon, tmp_dir=TMP, max_k=lib)
+        ref.build(fa, k, m, idx, canonical=canon, tmp_dir=TMP, max_k=lib, weighted=weighted)
         d = ref.RefDictionary(idx, max_k=lib)
         rng = np.random.default_rng(abs(hash(name)) % (2**32) if False else sum(map(ord, name)))
         pid, q = make_queries(d, rng, d.words)
@@ -178,6 +189,11 @@ def main():
         bases = "".join(reads).encode()
         offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
         sids, sfull, rep, _ = d.streaming_reads(bases, offs, full=True)
+        extra = {}
+        if weighted:   # dictionary::weight of the golden positives, of the first ids and of the last ones
+            wid = np.concatenate([pid, np.arange(0, 3000, dtype=np.uint64),
+                                  np.arange(d.num_kmers - 3000, d.num_kmers, dtype=np.uint64)])
+            extra = dict(weight_ids=wid, weights=d.weight(wid))
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"),
             queries=q, positive_ids=pid, ids=ids, ids_norc=ids_norc, full=full,
@@ -186,8 +202,9 @@ def main():
             stream_report=np.array([rep[n] for n in ("num_kmers", "num_positive_kmers", "num_negative_kmers",
                                                      "num_invalid_kmers", "num_searches", "num_extensions")],
                                    dtype=np.uint64),
+            **extra,
         )
-        manifest[name] = dict(source=src, k=k, m=m, canonical=canon, nseq=nseq, max_k=lib,
+        manifest[name] = dict(source=src, k=k, m=m, canonical=canon, nseq=nseq, max_k=lib, weighted=bool(weighted),
                               num_kmers=d.num_kmers, num_strings=d.num_strings,
                               index_bytes=os.path.getsize(idx), stream_report=rep,
                               num_found=int((ids != 2**64 - 1).sum()))

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import FIXTURES, REPORT_KEYS, golden
+from conftest import FIXTURES, REPORT_KEYS, WEIGHTED, golden
 
 pytestmark = pytest.mark.gpu
 
@@ -150,6 +150,36 @@ def test_streaming_device_buffers_and_file(dicts, name, tmp_path):
     assert d.streaming_query_from_file(str(tmp_path / "x.txt"))["num_kmers"] == 0  # unsupported extension
 
 
+@pytest.mark.parametrize("name", ["se_k31_m13", "sal100_k31_m11_canon", "se_k63_m21"])
+def test_streaming_multiline_fasta_vs_reference(dicts, name, tmp_path):
+    """streaming_query_from_fasta_file_multiline (src/query.cpp:9-51): all lines of a run -- header
+    lines included -- are concatenated and streamed without reset; only an empty line ends a run.
+    Expected counters come from the unmodified reference (oracle/_ref) on the same file."""
+    from oracle import ref
+    g, d = golden(name), dicts(name)
+    if not ref.available(g.max_k):
+        pytest.skip("oracle/_ref not built")
+    raw = g.z["read_bases"].tobytes().decode()
+    o = g.z["read_offsets"].astype(np.int64)
+    reads = [raw[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+    lines = []
+    for i, r in enumerate(reads):
+        if len(r) < 80:
+            continue                      # keep every run longer than k (the reference underflows otherwise, :22)
+        lines.append(">read%d some ACGT text" % i)
+        lines += [r[j:j + 60] for j in range(0, len(r), 60)]
+        if i % 7 == 3:
+            lines.append("")              # end of a run
+    fa = tmp_path / "multi.fa"
+    fa.write_text("\n".join(lines) + "\n")
+    rd = ref.RefDictionary(g.index, max_k=g.max_k)
+    want, _ = rd.streaming_file(str(fa), multiline=True)
+    rd.close()
+    got = d.streaming_query_from_file(str(fa), multiline=True)
+    assert [got[k] for k in REPORT_KEYS] == [want[k] for k in REPORT_KEYS]
+    assert got["num_positive_kmers"] > 1000 and got["num_invalid_kmers"] > 1000
+
+
 @pytest.mark.parametrize("name", FIXTURES)
 def test_navigational_queries(dicts, name):
     """kmer_neighbours / forward / backward / string_neighbours vs the reference's goldens, and the
@@ -174,6 +204,77 @@ def test_navigational_queries(dicts, name):
     same = full["string_id"][1:] == full["string_id"][:-1]
     assert ((nb[:-1, :4] == ids[1:, None]).any(axis=1) | ~same).all()
     assert ((nb[1:, 4:] == ids[:-1, None]).any(axis=1) | ~same).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_low_complexity_queries_vs_oracle(dicts, name):
+    """Homopolymers, short tandem repeats and indexed k-mers with a repeated m-mer: every m-mer hash
+    ties with another one, which is what the leftmost-minimum rule (util.hpp:262-283) is about and
+    what sends the kernel's 32-bit minimizer scan to its exact fallback."""
+    from oracle import port
+    g, d = golden(name), dicts(name)
+    o = port.OracleDictionary(g.index, g.max_k)
+    k, m, w = d.k(), d.m(), g.words
+    rng = np.random.default_rng(5)
+    vals = []
+    for period in range(1, 9):
+        for _ in range(40):
+            unit = rng.integers(0, 4, period)
+            x = 0
+            for i in range(k):
+                x |= int(unit[i % period]) << (2 * i)
+            vals.append(x)
+    # indexed k-mers whose minimizer-length substrings repeat
+    ids = rng.integers(0, d.num_kmers(), 300000).astype(np.uint64)
+    km = d.access_batch(ids).reshape(-1, w)
+    ints = [int(r[0]) | ((int(r[1]) << 64) if w == 2 else 0) for r in km[:60000]]
+    mask = (1 << (2 * m)) - 1
+    rep = [x for x in ints if len({(x >> (2 * i)) & mask for i in range(k - m + 1)}) < k - m + 1]
+    vals += rep[:3000]
+    full_mask = (1 << (2 * k)) - 1
+    vals += [(~x) & full_mask for x in vals[:320]] + [0, full_mask]
+    q = np.array([[x & (2**64 - 1), x >> 64][:w] for x in vals], dtype=np.uint64).reshape(-1)
+    want_ids, want_full = o.lookup(q, full=True)
+    got = d.lookup_batch(q, full=True)
+    for f in got.dtype.names:
+        assert (got[f] == want_full[f]).all(), f
+    assert (d.lookup_batch(q) == want_ids).all()
+    assert (d.lookup_batch(q, check_reverse_complement=False) == o.lookup(q, check_rc=False)).all()
+    o.close()
+
+
+@pytest.mark.parametrize("name", WEIGHTED)
+def test_weights(dicts, name):
+    """dictionary::weight (src/dictionary.cpp:96-100) vs the reference's goldens and, for every
+    k-mer id of the index, vs the C oracle; host and device buffers; lookup -> weight chain of
+    tools/perf.hpp:143-149."""
+    import torch
+    from oracle import port
+    g, d = golden(name), dicts(name)
+    assert d.weighted()
+    assert (d.weight_batch(g.z["weight_ids"]) == g.z["weights"]).all()
+    o = port.OracleDictionary(g.index, g.max_k)
+    ids = np.arange(d.num_kmers(), dtype=np.uint64)
+    want = o.weight(ids)
+    assert (d.weight_batch(ids) == want).all()
+    dev = d.weight_batch(torch.from_numpy(ids.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    assert (dev.cpu().numpy().view(np.uint64) == want).all()
+    npos = g.z["positive_ids"].size
+    q = torch.from_numpy(g.z["queries"].reshape(-1, g.words)[:npos].reshape(-1).view(np.int64)).cuda()
+    w = d.weight_batch(d.lookup_batch(q))
+    torch.cuda.synchronize()
+    assert (w.cpu().numpy().view(np.uint64) == g.z["weights"][:npos]).all()
+    assert d.weight(int(g.z["weight_ids"][0])) == int(g.z["weights"][0])
+    o.close()
+
+
+def test_weight_on_unweighted_dictionary_is_an_error(dicts):
+    import sshash_b200
+    d = dicts("se_k31_m13")
+    assert not d.weighted()
+    with pytest.raises(sshash_b200.SshashGpuError):
+        d.weight_batch(np.zeros(4, dtype=np.uint64))
 
 
 def test_edge_cases(dicts):

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import FIXTURES, REPORT_KEYS, golden
+from conftest import FIXTURES, REPORT_KEYS, WEIGHTED, golden
 from oracle import port, ref
 
 INVALID = np.uint64(2**64 - 1)
@@ -101,6 +101,53 @@ def test_navigational_queries_match_reference_golden(oracles, name):
     got = o.string_neighbours(z["string_ids"])
     for f in got.dtype.names:
         assert (got[f] == z["strings"][f]).all(), f
+
+
+@pytest.mark.parametrize("name", WEIGHTED)
+def test_weights_match_reference_golden(oracles, name):
+    """dictionary::weight (src/dictionary.cpp:96-100): golden weights come from the reference."""
+    g, o = golden(name), oracles(name)
+    assert o.weighted()
+    assert (o.weight(g.z["weight_ids"]) == g.z["weights"]).all()
+    assert np.unique(g.z["weights"]).size > 3
+
+
+def test_unweighted_index_reports_it(oracles):
+    assert not oracles("se_k31_m13").weighted()
+
+
+@pytest.mark.parametrize("name", ["se_k31_m13", "sal100_k31_m11_canon", "se_k63_m21"])
+def test_multiline_fasta_is_one_read_per_run(oracles, name, tmp_path):
+    """Restatement of streaming_query_from_fasta_file_multiline (src/query.cpp:9-51) used by the GPU
+    file driver: every run of non-empty lines (headers included) is ONE read.  Checked against the
+    unmodified reference on the same file."""
+    g, o = golden(name), oracles(name)
+    if not ref.available(g.max_k):
+        pytest.skip("oracle/_ref not built")
+    raw = g.z["read_bases"].tobytes().decode()
+    off = g.z["read_offsets"].astype(np.int64)
+    reads = [raw[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    lines, runs, cur = [], [], ""
+    for i, r in enumerate(reads):
+        if len(r) < 80:
+            continue
+        rec = [">read%d some ACGT text" % i] + [r[j:j + 60] for j in range(0, len(r), 60)]
+        lines += rec
+        cur += "".join(rec)
+        if i % 7 == 3:
+            lines.append("")
+            runs.append(cur)
+            cur = ""
+    if cur:
+        runs.append(cur)
+    fa = tmp_path / "multi.fa"
+    fa.write_text("\n".join(lines) + "\n")
+    rd = ref.RefDictionary(g.index, max_k=g.max_k)
+    want, _ = rd.streaming_file(str(fa), multiline=True)
+    rd.close()
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in runs])]).astype(np.uint64)
+    _, _, rep = o.streaming_reads("".join(runs).encode(), offs)
+    assert [rep[k] for k in REPORT_KEYS] == [want[k] for k in REPORT_KEYS]
 
 
 def test_bad_files(tmp_path):
