@@ -170,6 +170,14 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     ix.k = f.k; ix.m = f.m; ix.canonical = f.canonical ? 1 : 0;
     ix.kmer_words = max_k == 31 ? 1 : 2;
     ix.magic = f.hasher_magic;
+    for (uint32_t j = 0; j < 16; ++j) {
+        const uint32_t hi = static_cast<uint32_t>(f.hasher_magic >> 32) & ~63u;
+        ix.mini_left[j] = hi | j;
+        ix.mini_right[j] = hi | (63u - j);
+    }
+    ix.kmer_mask_lo = 2 * f.k >= 64 ? ~0ull : (1ull << (2 * f.k)) - 1;
+    ix.kmer_mask_hi = 2 * f.k <= 64 ? 0ull : (1ull << (2 * f.k - 64)) - 1;
+    ix.mmer_mask = 2 * f.m >= 64 ? ~0ull : (1ull << (2 * f.m)) - 1;
     ix.num_kmers = f.num_kmers; ix.num_strings = f.num_strings;
     ix.strings = static_cast<const uint64_t*>(up.raw(f.ptr(f.strings.data), f.strings.data.bytes()));
     ix.strings_bits = f.strings.num_bits;

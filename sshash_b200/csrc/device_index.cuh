@@ -96,6 +96,12 @@ struct DeviceIndex {
     uint32_t cw_code_bits;     // width of the reference's codeword inside a `codewords` entry
     uint32_t cw_fp_bits;       // fingerprint bits above it (0 = verbatim vector)
     uint32_t pad_;
+    // per-position constants of the minimizer scan (compute_minimizer_fast): (magic >> 32) with the
+    // low 6 bits replaced by J / 63 - J, J = position inside a 16-position word.  Indexed with
+    // compile-time J, so each is a constant-bank operand of the LOP3 that builds the key.
+    uint32_t mini_left[16], mini_right[16];
+    uint64_t kmer_mask_lo, kmer_mask_hi;   // low 2k bits set (second word: bits 64..2k-1)
+    uint64_t mmer_mask;                    // low 2m bits set
 };
 
 #ifdef __CUDACC__
@@ -184,6 +190,24 @@ __device__ __forceinline__ uint64_t read_word64(const uint64_t* __restrict__ dat
 __device__ __forceinline__ Kmer<1> read_kmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t k, Kmer<1>*) {
     return {read_word64(ix.strings, 2 * base_offset) & low_mask(2 * k)};
 }
+// the same for k == ix.k, with the mask precomputed on the host
+__device__ __forceinline__ Kmer<1> read_kmer(const DeviceIndex& ix, uint64_t base_offset, Kmer<1>*) {
+    return {read_word64(ix.strings, 2 * base_offset) & ix.kmer_mask_lo};
+}
+__device__ __forceinline__ Kmer<2> read_kmer(const DeviceIndex& ix, uint64_t base_offset, Kmer<2>*) {
+    uint64_t pos = 2 * base_offset, w = pos >> 6;
+    uint32_t s = (uint32_t)pos & 63u;
+    uint64_t a = ld64<false>(ix.strings + w), b = ld64<false>(ix.strings + w + 1);
+    Kmer<2> r;
+    if (s == 0) { r.lo = a; r.hi = b; }
+    else {
+        uint64_t c = ld64<false>(ix.strings + w + 2);
+        r.lo = (a >> s) | (b << (64 - s));
+        r.hi = (b >> s) | (c << (64 - s));
+    }
+    r.lo &= ix.kmer_mask_lo; r.hi &= ix.kmer_mask_hi;
+    return r;
+}
 __device__ __forceinline__ Kmer<2> read_kmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t k, Kmer<2>*) {
     uint64_t pos = 2 * base_offset, w = pos >> 6;
     uint32_t s = (uint32_t)pos & 63u;
@@ -200,7 +224,8 @@ __device__ __forceinline__ Kmer<2> read_kmer(const DeviceIndex& ix, uint64_t bas
     return r;
 }
 __device__ __forceinline__ uint64_t read_mmer(const DeviceIndex& ix, uint64_t base_offset, uint32_t m) {
-    return read_word64(ix.strings, 2 * base_offset) & low_mask(2 * m);
+    (void)m;
+    return read_word64(ix.strings, 2 * base_offset) & ix.mmer_mask;
 }
 
 // compact_vector::access, compact_vector.hpp:253-260 (two aligned word loads instead of one
@@ -278,12 +303,16 @@ __device__ __noinline__ Minimizer compute_minimizer_exact(Kmer<2> x, uint32_t k,
 }
 
 // FAST PATH.  x -> (x * C) mod 2^64 is a bijection (C is odd), so two m-mers have equal hashes only
-// if they are equal; the scan therefore compares only the HIGH 32 bits of each hash -- which needs
-// the high half of the product only, one xor, one 32-bit compare -- and raises `tie` whenever a
-// hash's high half equals the running minimum's.  Any m-mer whose high half ties with the final
-// minimum's raises it (whichever comes first sets the minimum, the other one hits the equality),
-// and only then (a repeated m-mer, or a 2^-32 accident) the exact 64-bit scan above runs.  The
-// m-mers are cut out of the k-mer's 32-bit words with one funnel shift each, 16 per word.
+// if they are equal; the scan therefore orders the m-mers by the HIGH 26 bits of their hashes only
+// (high half of the product, one xor) and proves afterwards that this was enough:
+//     key_left (p) = hash26(p) << 6 | p            min -> leftmost  position among the smallest hash26
+//     key_right(p) = hash26(p) << 6 | (63 - p)     min -> rightmost position among the smallest hash26
+// If both minima name the same position, exactly one m-mer has the smallest 26 high bits, hence
+// the smallest 64-bit hash: it is the minimizer.  Otherwise (a repeated m-mer, or two m-mers whose
+// hashes agree on 26 bits: 2^-26 per pair) the exact 64-bit scan above decides.
+// Cost per m-mer: funnel shift + mask + 2 IMAD (hash) + xor/mask + 2 adds + 2 min, positions and
+// shift amounts are immediates: the scan is unrolled 16 positions (= one 32-bit word of text) at a
+// time and the n mod 16 positions of the tail are entered through a switch.
 __device__ __forceinline__ void kmer_words32(Kmer<1> x, uint32_t (&r)[4]) {
     r[0] = (uint32_t)x.lo; r[1] = (uint32_t)(x.lo >> 32); r[2] = 0; r[3] = 0;
 }
@@ -295,45 +324,66 @@ __device__ __forceinline__ uint64_t kmer_bits_at(Kmer<2> x, uint32_t s) {   // s
     return s == 0 ? x.lo : (s < 64 ? ((x.lo >> s) | (x.hi << (64 - s))) : (x.hi >> (s - 64)));
 }
 
+template <bool SMALL_M, int J>
+__device__ __forceinline__ void minimizer_step(const DeviceIndex& ix, const uint32_t (&r)[4], uint32_t mm,
+                                               uint32_t& left, uint32_t& right) {
+    constexpr uint32_t c_lo = (uint32_t)SSHASH_MIX_C, c_hi = (uint32_t)(SSHASH_MIX_C >> 32);
+    uint32_t hh;
+    if (SMALL_M) {
+        const uint32_t w = __funnelshift_r(r[0], r[1], 2 * J) & mm;
+        hh = __umulhi(w, c_lo) + w * c_hi;
+    } else {
+        const uint32_t wl = __funnelshift_r(r[0], r[1], 2 * J);
+        const uint32_t wh = __funnelshift_r(r[1], r[2], 2 * J) & mm;
+        hh = __umulhi(wl, c_lo) + wl * c_hi + wh * c_lo;
+    }
+    // ((hh ^ magic_hi) & ~63) | J  ==  (hh & ~63) ^ mini_left[J]
+    left = min(left, (hh & ~63u) ^ ix.mini_left[J]);
+    right = min(right, (hh & ~63u) ^ ix.mini_right[J]);
+}
+
 template <int W, bool SMALL_M>
-__device__ __forceinline__ Minimizer compute_minimizer_fast(Kmer<W> x, uint32_t k, uint32_t m, uint64_t magic) {
-    const uint32_t n = k - m + 1;
-    const uint32_t c_lo = (uint32_t)SSHASH_MIX_C, c_hi = (uint32_t)(SSHASH_MIX_C >> 32);
-    const uint32_t magic_hi = (uint32_t)(magic >> 32);
+__device__ __forceinline__ Minimizer compute_minimizer_fast(const DeviceIndex& ix, Kmer<W> x) {
+    const uint32_t k = ix.k, m = ix.m;
+    const uint32_t n = k - m + 1;                      // <= 63
     const uint32_t mm = SMALL_M ? (uint32_t)low_mask(2 * m) : (uint32_t)low_mask(2 * m - 32);
     uint32_t r[4];
     kmer_words32(x, r);
-    uint32_t min_hi = 0xffffffffu, pos = 0;
-    bool tie = false;
-    for (uint32_t base = 0; base < n; base += 16) {
-        const uint32_t cnt = n - base < 16 ? n - base : 16;
-#pragma unroll 4
-        for (uint32_t j = 0; j < cnt; ++j) {
-            uint32_t hh;
-            if (SMALL_M) {
-                const uint32_t w = __funnelshift_r(r[0], r[1], 2 * j) & mm;
-                hh = __umulhi(w, c_lo) + w * c_hi;
-            } else {
-                const uint32_t wl = __funnelshift_r(r[0], r[1], 2 * j);
-                const uint32_t wh = __funnelshift_r(r[1], r[2], 2 * j) & mm;
-                hh = __umulhi(wl, c_lo) + wl * c_hi + wh * c_lo;
-            }
-            hh ^= magic_hi;
-            tie |= hh == min_hi;
-            if (hh < min_hi) { min_hi = hh; pos = base + j; }
-        }
+    uint32_t left = 0xffffffffu, right = 0xffffffffu;   // keys over global positions
+    uint32_t base = 0;
+#define SSHASH_STEP(J) minimizer_step<SMALL_M, J>(ix, r, mm, l, rt)
+    for (; base + 16 <= n; base += 16) {
+        uint32_t l = 0xffffffffu, rt = 0xffffffffu;    // keys over positions within this word
+        SSHASH_STEP(0); SSHASH_STEP(1); SSHASH_STEP(2); SSHASH_STEP(3); SSHASH_STEP(4); SSHASH_STEP(5);
+        SSHASH_STEP(6); SSHASH_STEP(7); SSHASH_STEP(8); SSHASH_STEP(9); SSHASH_STEP(10); SSHASH_STEP(11);
+        SSHASH_STEP(12); SSHASH_STEP(13); SSHASH_STEP(14); SSHASH_STEP(15);
+        left = min(left, l + base);
+        right = min(right, rt - base);
         r[0] = r[1]; r[1] = r[2]; r[2] = r[3]; r[3] = 0;
     }
-    if (tie) return compute_minimizer_exact<SMALL_M>(x, k, m, magic);
+    if (n & 15) {
+        uint32_t l = 0xffffffffu, rt = 0xffffffffu;
+        switch (n & 15) {                              // falls through: positions (n & 15) - 1 .. 0
+            case 15: SSHASH_STEP(14); case 14: SSHASH_STEP(13); case 13: SSHASH_STEP(12); case 12: SSHASH_STEP(11);
+            case 11: SSHASH_STEP(10); case 10: SSHASH_STEP(9); case 9: SSHASH_STEP(8); case 8: SSHASH_STEP(7);
+            case 7: SSHASH_STEP(6); case 6: SSHASH_STEP(5); case 5: SSHASH_STEP(4); case 4: SSHASH_STEP(3);
+            case 3: SSHASH_STEP(2); case 2: SSHASH_STEP(1); default: SSHASH_STEP(0);
+        }
+        left = min(left, l + base);
+        right = min(right, rt - base);
+    }
+#undef SSHASH_STEP
+    const uint32_t pos = left & 63u;
+    if (pos != 63u - (right & 63u)) return compute_minimizer_exact<SMALL_M>(x, k, m, ix.magic);
     return {kmer_bits_at(x, 2 * pos) & low_mask(2 * m), pos};
 }
 
 template <int W>
-__device__ __forceinline__ Minimizer compute_minimizer(Kmer<W> x, uint32_t k, uint32_t m, uint64_t magic) {
+__device__ __forceinline__ Minimizer compute_minimizer(const DeviceIndex& ix, Kmer<W> x) {
 #ifdef SSHASH_EXACT_MINIMIZER_ONLY   // A/B switch for measurements
-    return m <= 16 ? compute_minimizer_exact<true>(x, k, m, magic) : compute_minimizer_exact<false>(x, k, m, magic);
+    return ix.m <= 16 ? compute_minimizer_exact<true>(x, ix.k, ix.m, ix.magic) : compute_minimizer_exact<false>(x, ix.k, ix.m, ix.magic);
 #else
-    return m <= 16 ? compute_minimizer_fast<W, true>(x, k, m, magic) : compute_minimizer_fast<W, false>(x, k, m, magic);
+    return ix.m <= 16 ? compute_minimizer_fast<W, true>(ix, x) : compute_minimizer_fast<W, false>(ix, x);
 #endif
 }
 
@@ -483,11 +533,19 @@ __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<
     if (FULL) {
         if (read_mmer(ix, off0, m) != mi.value) { result_clear(res, heavy); return false; }
     }
-    for (uint32_t i = 0; i < n; ++i) {
-        uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
-        if (off < mi.pos) continue;
-        uint64_t ko = off - mi.pos;
-        if (!kmer_eq(read_kmer(ix, ko, k, (Kmer<W>*)nullptr), x)) continue;
+    // The candidate scan only COMPARES; the string is located once, after the scan, so that the
+    // lanes of a warp (most have a single candidate, a few a long mid-load bucket) reconverge
+    // before the end-point loads instead of each running them inside its own divergent iteration.
+    for (uint32_t i = 0;; ++i) {
+        uint64_t ko = 0;
+        bool hit = false;
+        for (; i < n; ++i) {
+            uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
+            if (off < mi.pos) continue;
+            ko = off - mi.pos;
+            if (kmer_eq(read_kmer(ix, ko, (Kmer<W>*)nullptr), x)) { hit = true; break; }
+        }
+        if (!hit) break;
         uint64_t sb, se;
         uint64_t sid = locate_string(ix, ko, sb, se);
         if (ko < se - k + 1) {                          // spss.hpp:233: reject k-mers spanning two strings
@@ -506,7 +564,7 @@ __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<
 
 template <int W, bool FULL>
 __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
-    return lookup_regular_with<W, FULL>(ix, x, compute_minimizer(x, ix.k, ix.m, ix.magic), res);
+    return lookup_regular_with<W, FULL>(ix, x, compute_minimizer(ix, x), res);
 }
 
 // Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)
@@ -524,27 +582,32 @@ __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kme
         uint64_t rm = read_mmer(ix, off0, m);
         if (rm != mi.value && rm != mmer_rc(mi.value, m)) { result_clear(res, heavy); return false; }
     }
-    for (uint32_t i = 0; i < n; ++i) {
-        uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            uint32_t p = t == 0 ? mi.pos : k - m - mi.pos;
+    // candidates in the reference's order: for each offset the forward position, then the mirrored
+    // one (spss.hpp:249-275); c = 2 * i + t.  Compare-only scan, located after reconvergence.
+    for (uint32_t c = 0;; ++c) {
+        uint64_t ko = 0;
+        bool hit = false, eq_r = false;
+        uint64_t off = 0;
+        for (; c < 2 * n; ++c) {
+            if ((c & 1) == 0) off = (c == 0) ? off0 : compact_get<false>(ix.mid_load, first + (c >> 1));
+            const uint32_t p = (c & 1) == 0 ? mi.pos : k - m - mi.pos;
             if (off < p) continue;
-            uint64_t ko = off - p;
-            Kmer<W> r = read_kmer(ix, ko, k, (Kmer<W>*)nullptr);
-            bool eq_f = kmer_eq(r, x), eq_r = kmer_eq(r, xr);
-            if (!eq_f && !eq_r) continue;
-            uint64_t sb, se;
-            uint64_t sid = locate_string(ix, ko, sb, se);
-            if (ko < se - k + 1) {
-                res.kmer_id = ko - sid * (k - 1);
-                res.kmer_id_in_string = ko - sb;
-                res.kmer_offset = ko;
-                res.kmer_orientation = eq_r ? -1 : 1;   // spss.hpp:263-264 (rc wins when both equal: impossible for odd k)
-                res.string_id = sid; res.string_begin = sb; res.string_end = se;
-                res.minimizer_found = 1;
-                return true;
-            }
+            ko = off - p;
+            const Kmer<W> r = read_kmer(ix, ko, (Kmer<W>*)nullptr);
+            eq_r = kmer_eq(r, xr);
+            if (kmer_eq(r, x) || eq_r) { hit = true; break; }
+        }
+        if (!hit) break;
+        uint64_t sb, se;
+        uint64_t sid = locate_string(ix, ko, sb, se);
+        if (ko < se - k + 1) {
+            res.kmer_id = ko - sid * (k - 1);
+            res.kmer_id_in_string = ko - sb;
+            res.kmer_offset = ko;
+            res.kmer_orientation = eq_r ? -1 : 1;       // spss.hpp:263-264 (rc wins when both equal: impossible for odd k)
+            res.string_id = sid; res.string_begin = sb; res.string_end = se;
+            res.minimizer_found = 1;
+            return true;
         }
     }
     result_clear(res, true);
@@ -556,8 +619,8 @@ template <int W, bool FULL>
 __device__ __forceinline__ bool lookup_canonical(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
     const uint32_t k = ix.k;
     Kmer<W> xr = kmer_rc(x, k);
-    Minimizer mf = compute_minimizer(x, k, ix.m, ix.magic);
-    Minimizer mr = compute_minimizer(xr, k, ix.m, ix.magic);
+    Minimizer mf = compute_minimizer(ix, x);
+    Minimizer mr = compute_minimizer(ix, xr);
     // the smaller minimizer decides; on a tie the forward info is tried first, then the rc info (:35-41)
     const bool tie = mf.value == mr.value;
     Minimizer mi = mr.value < mf.value ? mr : mf;
