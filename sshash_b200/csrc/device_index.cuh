@@ -582,20 +582,24 @@ __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kme
         uint64_t rm = read_mmer(ix, off0, m);
         if (rm != mi.value && rm != mmer_rc(mi.value, m)) { result_clear(res, heavy); return false; }
     }
-    // candidates in the reference's order: for each offset the forward position, then the mirrored
-    // one (spss.hpp:249-275); c = 2 * i + t.  Compare-only scan, located after reconvergence.
-    for (uint32_t c = 0;; ++c) {
+    // Candidates in the reference's order: for each offset the forward position pa, then the mirrored
+    // one pb (spss.hpp:249-275).  The two k-mers of an offset lie within k - m bases of each other
+    // (almost always the same 64-byte sector), so both are read up front -- independent loads, one
+    // latency -- and compared in order.  Compare-only scan, located after reconvergence; (i, t0)
+    // = where to resume should a match be rejected by the string-boundary test (spss.hpp:266).
+    const uint32_t pa = mi.pos, pb = k - m - mi.pos;
+    uint32_t i = 0, t0 = 0;
+    for (;;) {
         uint64_t ko = 0;
-        bool hit = false, eq_r = false;
-        uint64_t off = 0;
-        for (; c < 2 * n; ++c) {
-            if ((c & 1) == 0) off = (c == 0) ? off0 : compact_get<false>(ix.mid_load, first + (c >> 1));
-            const uint32_t p = (c & 1) == 0 ? mi.pos : k - m - mi.pos;
-            if (off < p) continue;
-            ko = off - p;
-            const Kmer<W> r = read_kmer(ix, ko, (Kmer<W>*)nullptr);
-            eq_r = kmer_eq(r, xr);
-            if (kmer_eq(r, x) || eq_r) { hit = true; break; }
+        bool hit = false, eq_r = false, second = false;
+        for (; i < n; ++i, t0 = 0) {
+            const uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
+            const bool va = t0 == 0 && off >= pa, vb = off >= pb;
+            Kmer<W> ra = x, rb = x;
+            if (va) ra = read_kmer(ix, off - pa, (Kmer<W>*)nullptr);
+            if (vb) rb = read_kmer(ix, off - pb, (Kmer<W>*)nullptr);
+            if (va && (kmer_eq(ra, x) || kmer_eq(ra, xr))) { ko = off - pa; eq_r = kmer_eq(ra, xr); hit = true; break; }
+            if (vb && (kmer_eq(rb, x) || kmer_eq(rb, xr))) { ko = off - pb; eq_r = kmer_eq(rb, xr); hit = true; second = true; break; }
         }
         if (!hit) break;
         uint64_t sb, se;
@@ -609,6 +613,7 @@ __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kme
             res.minimizer_found = 1;
             return true;
         }
+        if (second) { ++i; t0 = 0; } else t0 = 1;
     }
     result_clear(res, true);
     return false;

@@ -19,6 +19,13 @@ constexpr int kBlock = 256;
 // 6 resident CTAs/SM (<= 40 registers, 75 % occupancy): measured best on B200 for both the L2-resident
 // and the HBM-resident case (sweep over 3/4/5/6/8 in profiles/r1_notes.md)
 constexpr int kLookupMinBlocks = 6;
+// the canonical flow on 128-bit k-mers keeps x, its reverse complement and two candidate k-mers
+// live and spills ~100 bytes at 40 registers; measured on a 5e8-k-mer k=63 canonical index it is
+// still fastest with 6 resident CTAs (14.2 G lookups/s vs 13.4 with 5, 13.3 with 4)
+#ifndef SSHASH_WIDE_CANON_MINB
+#define SSHASH_WIDE_CANON_MINB 6
+#endif
+constexpr int kLookupMinBlocksWideCanon = SSHASH_WIDE_CANON_MINB;
 
 template <int W>
 __device__ __forceinline__ Kmer<W> load_kmer(const uint64_t* __restrict__ kmers, uint64_t i);
@@ -907,12 +914,12 @@ uint64_t kernel_launch_count() { return g_launches.load(); }
 cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const void* queries, bool ascii, uint64_t n, bool check_rc,
                           uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    const int grid = grid_for(n, ctx.sm_count, 2 * kLookupMinBlocks);
+    const int grid = grid_for(n, ctx.sm_count, 2 * (ix.canonical && ix.kmer_words == 2 ? kLookupMinBlocksWideCanon : kLookupMinBlocks));
     const int mode = member ? 2 : (full ? 1 : 0);
     const int crc = check_rc ? 1 : 0;
     cudaError_t err = cudaSuccess;
 #define SSHASH_LAUNCH(W, MODE, ASCII) \
-    err = ix.canonical ? launch(lookup_kernel<W, MODE, ASCII, true, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member) \
+    err = ix.canonical ? launch(lookup_kernel<W, MODE, ASCII, true, (W == 2 ? kLookupMinBlocksWideCanon : kLookupMinBlocks)>, grid, stream, ctx, ix, queries, n, crc, ids, full, member) \
                        : launch(lookup_kernel<W, MODE, ASCII, false, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
 #define SSHASH_DISPATCH_MODE(W, ASCII)                     \
     do {                                                   \

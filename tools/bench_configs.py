@@ -181,6 +181,11 @@ def main():
             r = lookup_config("cfg4 (scaled): synthetic 5e8 k-mers k63 m25", idx, 63, 248.0, 296.0)
             r["build_s"] = bs
             os.remove(idx)
+        elif c == "k63_canonical":
+            idx, bs = build_index(wd, 500000, 1062, 63, 25, canonical=True)
+            r = lookup_config("synthetic 5e8 k-mers k63 m25 canonical", idx, 63, 248.0, 248.0)
+            r["build_s"] = bs
+            os.remove(idx)
         elif c == "human":
             idx, bs = build_index(wd, 2500000, 1030, 31, 21)
             r = lookup_config("cfg5 index: synthetic human-scale 2.5e9 k-mers k31 m21", idx, 31, 208.0, 256.0)
