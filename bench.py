@@ -166,12 +166,13 @@ def scale_workload():
 
 def streaming_workload():
     """BASELINE.json configs[2]: streaming membership over 1e6 synthetic 150-bp reads (50 % hit) on
-    the cfg-1 index; windows/s device-resident and through the C ABI with host buffers, checked
-    against the C oracle on the first 20000 reads."""
+    the cfg-1 index; windows/s device-resident, through the C ABI with host buffers, and through
+    streaming_query_from_file on a 321 MB FASTQ file (records parsed on the GPU), checked against
+    the C oracle on the first 20000 reads and against the unmodified reference on a 1e5-read file."""
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import stream_bench
-        r = stream_bench.run(INDEX, 1_000_000)
+        r = stream_bench.run(INDEX, 1_000_000, files=True)
         r["workload"] = "cfg3: 1e6 synthetic 150-bp reads (1.2e8 windows), 50 % of reads from the index, cfg-1 index"
         return r
     except Exception as e:

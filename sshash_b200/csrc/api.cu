@@ -5,13 +5,18 @@
 #include <cuda_runtime.h>
 #include <zlib.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sshash_gpu.h"
@@ -64,6 +69,12 @@ struct Workspace {
     void* d_anchors = nullptr; uint64_t anchors_cap = 0;
     unsigned long long* d_counters = nullptr;
     unsigned long long* h_counters = nullptr;   // pinned
+    // file driver with device-side record parsing
+    uint8_t* d_raw = nullptr; uint64_t raw_cap = 0;
+    uint64_t* d_tiles = nullptr; uint64_t tiles_cap = 0;
+    uint64_t* d_line_start = nullptr; uint64_t ls_cap = 0;
+    uint64_t* d_spans = nullptr; uint64_t spans_cap = 0;
+    uint8_t* h_file[2] = {nullptr, nullptr}; uint64_t h_file_cap = 0;   // pinned
 
     ~Workspace() {
         for (auto& s : slots) {
@@ -75,6 +86,8 @@ struct Workspace {
         cudaFree(d_bases); cudaFree(d_read_offsets); cudaFree(d_win_offsets); cudaFree(d_block_sums);
         cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters); cudaFree(d_anchors);
         if (h_counters) cudaFreeHost(h_counters);
+        cudaFree(d_raw); cudaFree(d_tiles); cudaFree(d_line_start); cudaFree(d_spans);
+        for (auto* h : h_file) if (h) cudaFreeHost(h);
     }
 };
 
@@ -351,6 +364,9 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     }
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
     d->info.device_bytes = up.bytes;
+    // SSHASH_GPU_SPECULATE=0/1 forces the choice (measurements); default: indexes that do not fit L2
+    if (const char* e = std::getenv("SSHASH_GPU_SPECULATE")) ix.speculate_locate = e[0] == '1';
+    else ix.speculate_locate = up.bytes > (96ull << 20);
     return SSHASH_GPU_OK;
 }
 
@@ -641,8 +657,8 @@ int sshash_gpu_string_neighbours_batch(const sshash_gpu_dict* dict, const uint64
 }
 
 // One device-resident batch of reads: offsets scan, window lookups, state-machine replay.
-static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const char* d_bases, const uint64_t* d_read_offsets,
-                            uint64_t num_reads, uint64_t max_windows, uint64_t* d_ids_out, cudaStream_t s) {
+static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const char* d_bases, const uint64_t* d_read_begins,
+                            const uint64_t* d_read_ends, uint64_t num_reads, uint64_t max_windows, uint64_t* d_ids_out, cudaStream_t s) {
     const DeviceIndex& ix = dict->ix;
     CU(ensure(w.d_win_offsets, w.wo_cap, (num_reads + 2) * 8));
     CU(ensure(w.d_block_sums, w.bs_cap, window_offsets_scratch_words(num_reads) * 8));
@@ -657,8 +673,8 @@ static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const cha
     // SSHASH_GPU_STREAM_ALIGN=0 disables the anchor/alignment shortcut (every window is looked up)
     static const bool use_anchors = !(std::getenv("SSHASH_GPU_STREAM_ALIGN") && std::getenv("SSHASH_GPU_STREAM_ALIGN")[0] == '0');
     if (use_anchors) CU(ensure(w.d_anchors, w.anchors_cap, streaming_anchor_bytes(num_reads)));
-    CU(launch_window_offsets(ix.k, d_read_offsets, num_reads, w.d_win_offsets, w.d_block_sums, s));
-    CU(launch_streaming(ix, dict->ctx, d_bases, d_read_offsets, w.d_win_offsets, num_reads, use_anchors ? w.d_anchors : nullptr,
+    CU(launch_window_offsets(ix.k, d_read_begins, d_read_ends, num_reads, w.d_win_offsets, w.d_block_sums, s));
+    CU(launch_streaming(ix, dict->ctx, d_bases, d_read_begins, d_read_ends, w.d_win_offsets, num_reads, use_anchors ? w.d_anchors : nullptr,
                         w.d_win_id, w.d_win_aux, d_ids_out, max_windows, w.d_counters, s));
     return SSHASH_GPU_OK;
 }
@@ -690,7 +706,7 @@ int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, c
         CU(cudaMemcpyAsync(&first, read_offsets, 8, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(&last, read_offsets + num_reads, 8, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        st = streaming_device(dict, w, bases, read_offsets, num_reads, last - first + 1, kmer_ids, s);
+        st = streaming_device(dict, w, bases, read_offsets, read_offsets + 1, num_reads, last - first + 1, kmer_ids, s);
         if (st) return st;
     } else {
         // chunks of reads: <= 64 MB of bases each, staged through the workspace buffers
@@ -710,7 +726,7 @@ int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, c
             if (kmer_ids) CU(ensure(w.d_ids, w.ids_cap, (nwin + 1) * 8));
             CU(cudaMemcpyAsync(w.d_bases, bases + read_offsets[r0], nb, cudaMemcpyHostToDevice, s));
             CU(cudaMemcpyAsync(w.d_read_offsets, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, s));
-            st = streaming_device(dict, w, static_cast<const char*>(w.d_bases), w.d_read_offsets, nr, nwin + 1,
+            st = streaming_device(dict, w, static_cast<const char*>(w.d_bases), w.d_read_offsets, w.d_read_offsets + 1, nr, nwin + 1,
                                   kmer_ids ? w.d_ids : nullptr, s);
             if (st) return st;
             if (kmer_ids && nwin) CU(cudaMemcpyAsync(kmer_ids + win_done, w.d_ids, nwin * 8, cudaMemcpyDeviceToHost, s));
@@ -729,6 +745,213 @@ int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, c
     report->num_positive_kmers = report->num_searches + report->num_extensions;   // streaming_query.hpp:113
     return SSHASH_GPU_OK;
 }
+
+}  // extern "C"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// File driver with DEVICE-side record parsing (FASTQ, single-line FASTA; plain or gzip).
+// The host only moves bytes: a reader thread fills two pinned buffers (parallel pread for plain
+// files, zlib inflate for .gz), each chunk is copied to HBM as is, the GPU finds the lines and
+// the sequence spans (kernels.cu, "record parsing") and the streaming kernels run on the raw bytes.
+// Per chunk the host learns one number (how many lines the chunk holds) and carries the bytes of
+// the unfinished last record over to the next chunk.
+// ------------------------------------------------------------------------------------------------
+class ChunkReader {
+public:
+    ~ChunkReader() { if (gz_) gzclose(gz_); else if (fd_ >= 0) ::close(fd_); }
+    bool open(const char* filename) {
+        fd_ = ::open(filename, O_RDONLY);
+        if (fd_ < 0) return false;
+        unsigned char magic[2] = {0, 0};
+        const ssize_t got = ::pread(fd_, magic, 2, 0);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            gz_ = gzdopen(fd_, "rb");
+            if (!gz_) return false;
+            gzbuffer(gz_, 1 << 20);
+        }
+        return true;
+    }
+    // up to n bytes into dst; returns the number read (< n only at end of file), -1 on error
+    int64_t read(uint8_t* dst, uint64_t n) {
+        if (gz_) {
+            uint64_t done = 0;
+            while (done < n) {
+                const int r = gzread(gz_, dst + done, (unsigned)std::min<uint64_t>(n - done, 1u << 30));
+                if (r < 0) return -1;
+                if (r == 0) break;
+                done += (uint64_t)r;
+            }
+            return (int64_t)done;
+        }
+        // plain file: the page-cache copy is the bottleneck of one thread, so slices are read in parallel
+        const unsigned hw = std::thread::hardware_concurrency();
+        const uint64_t nt = n >= (4u << 20) ? std::max(1u, std::min(8u, hw ? hw : 1u)) : 1;
+        const uint64_t slice = (n + nt - 1) / nt;
+        std::vector<int64_t> got(nt, 0);
+        auto work = [&](uint64_t t) {
+            const uint64_t b = t * slice, e = std::min(n, b + slice);
+            uint64_t done = b;
+            while (done < e) {
+                const ssize_t r = ::pread(fd_, dst + done, e - done, (off_t)(pos_ + done));
+                if (r < 0) { got[t] = -1; return; }
+                if (r == 0) break;
+                done += (uint64_t)r;
+            }
+            got[t] = (int64_t)(done - b);
+        };
+        std::vector<std::thread> th;
+        for (uint64_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        uint64_t total = 0;
+        for (uint64_t t = 0; t < nt; ++t) {
+            if (got[t] < 0) return -1;
+            total += (uint64_t)got[t];
+            if ((uint64_t)got[t] < std::min(n, (t + 1) * slice) - std::min(n, t * slice)) break;   // end of file inside this slice
+        }
+        pos_ += total;
+        return (int64_t)total;
+    }
+private:
+    int fd_ = -1;
+    gzFile gz_ = nullptr;
+    uint64_t pos_ = 0;
+};
+
+uint64_t env_bytes(const char* name, uint64_t dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    const unsigned long long v = std::strtoull(e, nullptr, 10);
+    return v ? v : dflt;
+}
+
+// *need_host_parser = true (and OK returned) when a single record does not fit a chunk: the caller
+// then runs the host line parser over the whole file instead.
+int stream_file_device_parse(const sshash_gpu_dict* dict, const char* filename, bool fastq, sshash_streaming_report* report,
+                             bool* need_host_parser) {
+    *need_host_parser = false;
+    // SSHASH_GPU_FILE_CHUNK: bytes per chunk (tests use tiny chunks to exercise the record carry-over)
+    const uint64_t chunk = std::max<uint64_t>(64, env_bytes("SSHASH_GPU_FILE_CHUNK", 32ull << 20));
+    const uint64_t carry_max = chunk;
+    const uint32_t stride = fastq ? 4 : 2;
+    ChunkReader reader;
+    if (!reader.open(filename)) return fail(SSHASH_GPU_EIO, std::string("error in opening the file '") + filename + "'");
+
+    WorkspaceLease ws(dict);
+    Workspace& w = *ws.w;
+    const uint64_t host_cap = carry_max + chunk + 64;
+    if (w.h_file_cap < host_cap) {
+        for (auto*& h : w.h_file) { if (h) cudaFreeHost(h); h = nullptr; }
+        w.h_file_cap = 0;
+        for (auto*& h : w.h_file) CU(cudaMallocHost(reinterpret_cast<void**>(&h), host_cap));
+        w.h_file_cap = host_cap;
+    }
+    if (!w.d_counters) {
+        CU(cudaMalloc(reinterpret_cast<void**>(&w.d_counters), 8 * sizeof(unsigned long long)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&w.h_counters), 8 * sizeof(unsigned long long)));
+    }
+    cudaStream_t s = dict->stream;
+    CU(cudaMemsetAsync(w.d_counters, 0, 8 * sizeof(unsigned long long), s));
+
+    // reader thread: fills slot 0, 1, 0, ... at offset carry_max, hands each over with its byte count
+    struct Handoff {
+        std::mutex mu; std::condition_variable cv;
+        int64_t filled[2] = {-2, -2};   // -2 = free, -1 = read error, >= 0 = bytes read
+        bool stop = false;
+    } ho;
+    std::thread rd([&] {
+        for (int slot = 0;; slot ^= 1) {
+            {
+                std::unique_lock<std::mutex> lk(ho.mu);
+                ho.cv.wait(lk, [&] { return ho.filled[slot] == -2 || ho.stop; });
+                if (ho.stop) return;
+            }
+            const int64_t n = reader.read(w.h_file[slot] + carry_max, chunk);
+            {
+                std::lock_guard<std::mutex> lk(ho.mu);
+                ho.filled[slot] = n;
+            }
+            ho.cv.notify_all();
+            if (n < (int64_t)chunk) return;   // error or end of file
+        }
+    });
+    struct Joiner {
+        std::thread& t; Handoff& h;
+        ~Joiner() { { std::lock_guard<std::mutex> lk(h.mu); h.stop = true; } h.cv.notify_all(); if (t.joinable()) t.join(); }
+    } joiner{rd, ho};
+
+    std::vector<uint8_t> carry;
+    int st = SSHASH_GPU_OK;
+    for (int slot = 0;; slot ^= 1) {
+        int64_t got;
+        {
+            std::unique_lock<std::mutex> lk(ho.mu);
+            ho.cv.wait(lk, [&] { return ho.filled[slot] != -2; });
+            got = ho.filled[slot];
+        }
+        if (got < 0) return fail(SSHASH_GPU_EIO, std::string("error in reading the file '") + filename + "'");
+        const bool eof = (uint64_t)got < chunk;
+        uint8_t* begin = w.h_file[slot] + carry_max - carry.size();
+        if (!carry.empty()) std::memcpy(begin, carry.data(), carry.size());
+        uint64_t n = carry.size() + (uint64_t)got;
+        if (eof) {   // terminate the last line and complete the last record (missing lines read as empty, query.cpp:86-107)
+            std::memset(begin + n, '\n', stride + 1);
+            n += stride + 1;
+        }
+        const uint64_t tiles = parse_tiles(n);
+        CU(ensure(w.d_raw, w.raw_cap, n + 64));
+        CU(ensure(w.d_tiles, w.tiles_cap, (tiles + 2) * 8));
+        CU(cudaMemcpyAsync(w.d_raw, begin, n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(w.d_tiles + tiles, 0, 8, s));
+        CU(launch_count_lines(w.d_raw, n, w.d_tiles, s));
+        CU(cudaMemcpyAsync(w.h_counters + 6, w.d_tiles + tiles, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        const uint64_t lines = w.h_counters[6], records = lines / stride;
+        if (records == 0 && !eof) { *need_host_parser = true; return SSHASH_GPU_OK; }
+        // the unfinished record: everything after the newline that ends line stride * records - 1
+        carry.clear();
+        if (!eof) {
+            uint64_t cut = n;
+            for (uint64_t q = lines - stride * records + 1; q; --q) {
+                const void* nl = memrchr(begin, '\n', cut);
+                cut = (uint64_t)(static_cast<const uint8_t*>(nl) - begin);
+            }
+            cut += 1;
+            carry.assign(begin + cut, begin + n);
+            if (carry.size() > carry_max) { *need_host_parser = true; return SSHASH_GPU_OK; }
+        }
+        {   // the pinned slot has been copied and the carry saved: hand it back to the reader
+            std::lock_guard<std::mutex> lk(ho.mu);
+            ho.filled[slot] = -2;
+        }
+        ho.cv.notify_all();
+        if (records) {
+            CU(ensure(w.d_line_start, w.ls_cap, (lines + 2) * 8));
+            CU(ensure(w.d_spans, w.spans_cap, 2 * records * 8));
+            CU(launch_read_spans(w.d_raw, n, w.d_tiles, w.d_line_start, records, stride, w.d_spans, w.d_spans + records,
+                                 dict->ctx.sm_count, s));
+            st = streaming_device(dict, w, reinterpret_cast<const char*>(w.d_raw), w.d_spans, w.d_spans + records, records, n + 1,
+                                  nullptr, s);
+            if (st) return st;
+        }
+        if (eof) break;
+    }
+    CU(cudaMemcpyAsync(w.h_counters, w.d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    report->num_kmers = w.h_counters[0];
+    report->num_searches = w.h_counters[1];
+    report->num_extensions = w.h_counters[2];
+    report->num_negative_kmers = w.h_counters[3];
+    report->num_invalid_kmers = w.h_counters[4];
+    report->num_positive_kmers = report->num_searches + report->num_extensions;
+    return SSHASH_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 // Host-side file driver: same record structure as the reference's drivers (src/query.cpp:53-108):
 // FASTA = header line + one sequence line per record, FASTQ = 4 lines per record; gz through zlib.
@@ -751,6 +974,14 @@ int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char
         return SSHASH_GPU_OK;
     }
     if (multiline && fastq) multiline = 0;   // query.cpp:154-163: the flag only affects FASTA input
+    // default: records are parsed on the GPU.  SSHASH_GPU_HOST_PARSER=1 (or multiline FASTA, or a
+    // record that does not fit one chunk) takes the host line parser below.
+    if (!multiline && !(std::getenv("SSHASH_GPU_HOST_PARSER") && std::getenv("SSHASH_GPU_HOST_PARSER")[0] == '1')) {
+        bool need_host_parser = false;
+        st = stream_file_device_parse(dict, filename, fastq, report, &need_host_parser);
+        if (st || !need_host_parser) return st;
+        std::memset(report, 0, sizeof(*report));
+    }
     gzFile gz = gzopen(filename, "rb");   // transparently reads uncompressed files too
     if (!gz) return fail(SSHASH_GPU_EIO, "error in opening the file '" + fn + "'");
     gzbuffer(gz, 1 << 20);

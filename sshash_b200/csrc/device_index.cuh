@@ -102,6 +102,12 @@ struct DeviceIndex {
     uint32_t mini_left[16], mini_right[16];
     uint64_t kmer_mask_lo, kmer_mask_hi;   // low 2k bits set (second word: bits 64..2k-1)
     uint64_t mmer_mask;                    // low 2m bits set
+    // 1 = launch the lookup kernels that issue the end-point probe of the first candidate next to its
+    // k-mer read (lookup_regular_with<SPEC>).  Pays when `strings` lives in HBM (+3.5 % on a
+    // 5e8-k-mer index), costs 2.5 % when the whole index is L2-resident and the kernel is
+    // issue-bound; set at open time from the index size (host-side dispatch only).
+    uint32_t speculate_locate;
+    uint32_t pad2_;
 };
 
 #ifdef __CUDACC__
@@ -448,6 +454,22 @@ __device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_
     begin = cur; end = next;
     return i;
 }
+// The same in two halves, so that the directory and end-point loads of the FIRST candidate (the only
+// one in a singleton bucket) are in flight together with the cold read of its k-mer from `strings`
+// instead of starting after the comparison: two L2 round trips off the dependent chain.
+struct LocateProbe { uint64_t i, cur, next; };
+__device__ __forceinline__ LocateProbe locate_begin(const DeviceIndex& ix, uint64_t x) {
+    LocateProbe p;
+    p.i = ld32<true>(ix.ends_dir + (x >> ix.dir_shift));
+    p.cur = ld64<true>(ix.ends + p.i);
+    p.next = ld64<true>(ix.ends + p.i + 1);
+    return p;
+}
+__device__ __forceinline__ uint64_t locate_finish(const DeviceIndex& ix, LocateProbe p, uint64_t x, uint64_t& begin, uint64_t& end) {
+    while (p.next <= x) { p.cur = p.next; ++p.i; p.next = ld64<true>(ix.ends + p.i + 1); }
+    begin = p.cur; end = p.next;
+    return p.i;
+}
 
 // ------------------------------------------------------------------------------------------------
 // one lookup
@@ -523,7 +545,7 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
 // FULL = also produce minimizer_found exactly (needs the m-mer check of spss.hpp:46-65); without
 // it the k-mer comparison alone decides, which yields the same ids (a k-mer match implies the
 // m-mer match because the minimizer is a substring of the k-mer at pos_in_kmer).
-template <int W, bool FULL>
+template <int W, bool FULL, bool SPEC = false>
 __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<W> x, Minimizer mi, LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     uint64_t first; bool heavy;
@@ -536,18 +558,30 @@ __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<
     // The candidate scan only COMPARES; the string is located once, after the scan, so that the
     // lanes of a warp (most have a single candidate, a few a long mid-load bucket) reconverge
     // before the end-point loads instead of each running them inside its own divergent iteration.
+    // SPEC: the end-point probe of the first candidate is issued speculatively, next to its k-mer read.
+    LocateProbe probe{0, 0, 0};
+    Kmer<W> r0 = x;
+    const bool v0 = off0 >= mi.pos;
+    if (SPEC && v0) {
+        r0 = read_kmer(ix, off0 - mi.pos, (Kmer<W>*)nullptr);
+        probe = locate_begin(ix, off0 - mi.pos);
+    }
     for (uint32_t i = 0;; ++i) {
         uint64_t ko = 0;
         bool hit = false;
-        for (; i < n; ++i) {
-            uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
-            if (off < mi.pos) continue;
-            ko = off - mi.pos;
-            if (kmer_eq(read_kmer(ix, ko, (Kmer<W>*)nullptr), x)) { hit = true; break; }
+        if (SPEC && i == 0 && v0 && kmer_eq(r0, x)) { ko = off0 - mi.pos; hit = true; }
+        else {
+            if (SPEC && i == 0) i = 1;
+            for (; i < n; ++i) {
+                uint64_t off = (!SPEC && i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
+                if (off < mi.pos) continue;
+                ko = off - mi.pos;
+                if (kmer_eq(read_kmer(ix, ko, (Kmer<W>*)nullptr), x)) { hit = true; break; }
+            }
         }
         if (!hit) break;
         uint64_t sb, se;
-        uint64_t sid = locate_string(ix, ko, sb, se);
+        uint64_t sid = (SPEC && i == 0) ? locate_finish(ix, probe, ko, sb, se) : locate_string(ix, ko, sb, se);
         if (ko < se - k + 1) {                          // spss.hpp:233: reject k-mers spanning two strings
             res.kmer_id = ko - sid * (k - 1);
             res.kmer_id_in_string = ko - sb;
@@ -562,9 +596,9 @@ __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<
     return false;
 }
 
-template <int W, bool FULL>
+template <int W, bool FULL, bool SPEC = false>
 __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
-    return lookup_regular_with<W, FULL>(ix, x, compute_minimizer(ix, x), res);
+    return lookup_regular_with<W, FULL, SPEC>(ix, x, compute_minimizer(ix, x), res);
 }
 
 // Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)

@@ -108,7 +108,7 @@ template <> struct RcQueue<2> {
 // 32 are parked (or the input is exhausted), 32 parked reverse complements.  CANON selects the
 // canonical (src/dictionary.cpp:24-56) or the regular (:7-22, :64-78) flow at compile time so that
 // each instantiation carries only its own path.
-template <int W, int MODE, bool ASCII, bool CANON, int MINB>
+template <int W, int MODE, bool ASCII, bool CANON, int MINB, bool SPEC = false>
 __global__ void __launch_bounds__(kBlock, MINB)
 lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
               uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
@@ -147,7 +147,7 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
         LookupResult r;
         if (active) {
             if (CANON) found = lookup_canonical<W, FULL>(ix, x, r);
-            else found = lookup_regular<W, FULL>(ix, x, r);
+            else found = lookup_regular<W, FULL, SPEC>(ix, x, r);
         }
         const bool park = active && fresh && two_pass && !found;
         if (active && !park) {
@@ -401,12 +401,13 @@ struct Anchor { int64_t diag; uint64_t info; };   // info: bit 63 valid, bit 62 
 template <int W>
 __global__ void __launch_bounds__(kBlock, 4)
 stream_anchor_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
-                     const uint64_t* __restrict__ read_offsets, uint64_t num_reads, Anchor* __restrict__ anchors) {
+                     const uint64_t* __restrict__ read_begins, const uint64_t* __restrict__ read_ends, uint64_t num_reads,
+                     Anchor* __restrict__ anchors) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint32_t k = ix.k;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < num_reads * kAnchorsPerRead; t += stride) {
         const uint64_t r = t / kAnchorsPerRead, s = t % kAnchorsPerRead;
-        const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
+        const uint64_t b = read_begins[r], len = read_ends[r] - b;
         Anchor a{0, 0};
         if (len >= k) {
             const uint64_t nwin = len - k + 1, p = s * (nwin / kAnchorsPerRead);
@@ -430,7 +431,8 @@ stream_anchor_kernel(const __grid_constant__ DeviceIndex ix, const char* __restr
 template <int W>
 __global__ void __launch_bounds__(kBlock, 4)
 stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
-                      const uint64_t* __restrict__ read_offsets, const uint64_t* __restrict__ win_offsets,
+                      const uint64_t* __restrict__ read_begins, const uint64_t* __restrict__ read_ends,
+                      const uint64_t* __restrict__ win_offsets,
                       uint64_t num_reads, const Anchor* __restrict__ anchors, uint64_t* __restrict__ win_id,
                       uint64_t* __restrict__ win_aux, unsigned long long* __restrict__ next_read) {
     __shared__ uint64_t hash_f[kBlock / 32][kTilePositions];
@@ -456,7 +458,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
         if (claim >= num_reads) break;
         const uint64_t claim_end = claim + kReadsPerClaim < num_reads ? claim + kReadsPerClaim : num_reads;
     for (uint64_t r = claim; r < claim_end; ++r) {
-        const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
+        const uint64_t b = read_begins[r], len = read_ends[r] - b;
         if (len < k) continue;
         const uint64_t nwin = len - k + 1, w0 = win_offsets[r];
         const char* s = bases + b;
@@ -681,14 +683,15 @@ template <> struct RollingKmer<2> {
 template <int W>
 __global__ void __launch_bounds__(kBlock)
 stream_scan_kernel(const __grid_constant__ DeviceIndex ix, const char* __restrict__ bases,
-                   const uint64_t* __restrict__ read_offsets, const uint64_t* __restrict__ win_offsets,
+                   const uint64_t* __restrict__ read_begins, const uint64_t* __restrict__ read_ends,
+                   const uint64_t* __restrict__ win_offsets,
                    uint64_t num_reads, const uint64_t* __restrict__ win_id, const uint64_t* __restrict__ win_aux,
                    uint64_t* __restrict__ ids_out, unsigned long long* __restrict__ counters) {
     const uint32_t k = ix.k;
     unsigned long long n_search = 0, n_ext = 0, n_neg = 0, n_inv = 0, n_kmers = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_reads; r += stride) {
-        const uint64_t b = read_offsets[r], len = read_offsets[r + 1] - b;
+        const uint64_t b = read_begins[r], len = read_ends[r] - b;
         if (len < k) continue;
         const uint64_t nwin = len - k + 1, w0 = win_offsets[r];
         n_kmers += nwin;
@@ -812,9 +815,13 @@ stream_classify_kernel(const uint64_t* __restrict__ win_offsets, uint64_t num_re
 constexpr int kScanItems = 8;                       // reads per thread
 constexpr int kScanTile = kBlock * kScanItems;      // reads per block
 
-__device__ __forceinline__ uint64_t windows_of(const uint64_t* __restrict__ ro, uint64_t r, uint64_t num_reads, uint32_t k) {
+// Reads are given as spans: read r = bases[read_begins[r], read_ends[r]).  Contiguous reads pass
+// (read_offsets, read_offsets + 1); the device-side FASTA/FASTQ parser passes the spans of the
+// sequence lines inside the raw file bytes.
+__device__ __forceinline__ uint64_t windows_of(const uint64_t* __restrict__ rb, const uint64_t* __restrict__ re, uint64_t r,
+                                               uint64_t num_reads, uint32_t k) {
     if (r >= num_reads) return 0;
-    uint64_t len = ro[r + 1] - ro[r];
+    uint64_t len = re[r] - rb[r];
     return len >= k ? len - k + 1 : 0;
 }
 
@@ -838,9 +845,10 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t& t
 }
 
 __global__ void __launch_bounds__(kBlock)
-win_block_sums_kernel(uint32_t k, const uint64_t* __restrict__ ro, uint64_t num_reads, uint64_t* __restrict__ block_sums) {
+win_block_sums_kernel(uint32_t k, const uint64_t* __restrict__ rb, const uint64_t* __restrict__ re, uint64_t num_reads,
+                      uint64_t* __restrict__ block_sums) {
     uint64_t r0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems, s = 0;
-    for (int j = 0; j < kScanItems; ++j) s += windows_of(ro, r0 + j, num_reads, k);
+    for (int j = 0; j < kScanItems; ++j) s += windows_of(rb, re, r0 + j, num_reads, k);
     uint64_t total;
     block_exclusive_scan(s, total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -859,11 +867,11 @@ win_scan_sums_kernel(uint64_t* __restrict__ block_sums, uint64_t nblocks) {   //
 }
 
 __global__ void __launch_bounds__(kBlock)
-win_offsets_kernel(uint32_t k, const uint64_t* __restrict__ ro, uint64_t num_reads, const uint64_t* __restrict__ block_sums,
-                   uint64_t* __restrict__ win_offsets) {
+win_offsets_kernel(uint32_t k, const uint64_t* __restrict__ rb, const uint64_t* __restrict__ re, uint64_t num_reads,
+                   const uint64_t* __restrict__ block_sums, uint64_t* __restrict__ win_offsets) {
     uint64_t r0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems, s = 0;
     uint64_t c[kScanItems];
-    for (int j = 0; j < kScanItems; ++j) { c[j] = windows_of(ro, r0 + j, num_reads, k); s += c[j]; }
+    for (int j = 0; j < kScanItems; ++j) { c[j] = windows_of(rb, re, r0 + j, num_reads, k); s += c[j]; }
     uint64_t total;
     uint64_t off = block_sums[blockIdx.x] + block_exclusive_scan(s, total);
     for (int j = 0; j < kScanItems; ++j) {
@@ -872,6 +880,70 @@ win_offsets_kernel(uint32_t k, const uint64_t* __restrict__ ro, uint64_t num_rea
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Device-side FASTA / FASTQ record parsing (the step before the path; the reference's drivers,
+// src/query.cpp:53-108, call std::getline per line on the host).  Input: a chunk of raw file bytes
+// in HBM.  Records are POSITIONAL, exactly as in the reference: FASTQ = 4 lines per record with the
+// sequence on the 2nd, FASTA = 2 lines per record with the sequence on the 2nd; no character of a
+// header/quality line is ever interpreted.  Three small kernels index the newlines
+//   newline_count_kernel     '\n' per 4 KB tile (16 bytes per thread, one 128-bit load)
+//   win_scan_sums_kernel     exclusive scan of the tile counts (+ grand total = number of lines)
+//   newline_positions_kernel line_start[j + 1] = position after the j-th newline
+// and read_spans_kernel turns lines into read spans [begin, end) over the raw bytes, which the
+// streaming kernels consume in place: bases are never copied or compacted.
+// ------------------------------------------------------------------------------------------------
+constexpr int kParseBytesPerThread = 16;
+constexpr int kParseTile = kBlock * kParseBytesPerThread;
+
+// bit j set <=> raw[p + j] == '\n' (p is 16-byte aligned; bytes at or beyond n do not count)
+__device__ __forceinline__ uint32_t newline_mask16(const uint8_t* __restrict__ raw, uint64_t p, uint64_t n) {
+    if (p >= n) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + p));   // the buffer is padded to 16 bytes
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t e = __vcmpeq4(w[i], 0x0a0a0a0au);             // 0xff in every matching byte
+        mask |= (((e >> 7) & 1u) | ((e >> 14) & 2u) | ((e >> 21) & 4u) | ((e >> 28) & 8u)) << (4 * i);
+    }
+    const uint64_t left = n - p;
+    return left >= 16 ? mask : mask & ((1u << left) - 1u);
+}
+
+__global__ void __launch_bounds__(kBlock)
+newline_count_kernel(const uint8_t* __restrict__ raw, uint64_t n, uint64_t* __restrict__ tile_counts) {
+    const uint64_t p = (uint64_t)blockIdx.x * kParseTile + (uint64_t)threadIdx.x * kParseBytesPerThread;
+    uint64_t total;
+    block_exclusive_scan(__popc(newline_mask16(raw, p, n)), total);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kBlock)
+newline_positions_kernel(const uint8_t* __restrict__ raw, uint64_t n, const uint64_t* __restrict__ tile_offsets,
+                         uint64_t* __restrict__ line_start) {
+    const uint64_t p = (uint64_t)blockIdx.x * kParseTile + (uint64_t)threadIdx.x * kParseBytesPerThread;
+    uint32_t mask = newline_mask16(raw, p, n);
+    uint64_t total;
+    uint64_t rank = tile_offsets[blockIdx.x] + block_exclusive_scan(__popc(mask), total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = 0;
+    while (mask) {
+        const uint32_t j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        line_start[++rank] = p + j + 1;
+    }
+}
+
+// record r = lines [stride * r, stride * (r + 1)); its sequence is line stride * r + 1, without the '\n'
+__global__ void __launch_bounds__(kBlock)
+read_spans_kernel(const uint64_t* __restrict__ line_start, uint64_t num_records, uint32_t stride,
+                  uint64_t* __restrict__ read_begins, uint64_t* __restrict__ read_ends) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_records; r += step) {
+        read_begins[r] = line_start[stride * r + 1];
+        read_ends[r] = line_start[stride * r + 2] - 1;
+    }
+}
 
 std::atomic<uint64_t> g_launches{0};
 
@@ -923,7 +995,10 @@ cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const voi
                        : launch(lookup_kernel<W, MODE, ASCII, false, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
 #define SSHASH_DISPATCH_MODE(W, ASCII)                     \
     do {                                                   \
-        if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);         \
+        if (mode == 0 && !ix.canonical && ix.speculate_locate)                                                          \
+            err = launch(lookup_kernel<W, 0, ASCII, false, kLookupMinBlocks, true>, grid, stream, ctx, ix, queries, n, crc, \
+                         ids, full, member);                                                                            \
+        else if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);    \
         else if (mode == 1) SSHASH_LAUNCH(W, 1, ASCII);    \
         else SSHASH_LAUNCH(W, 2, ASCII);                   \
     } while (0)
@@ -978,18 +1053,18 @@ uint64_t streaming_anchor_bytes(uint64_t num_reads) { return num_reads * kAnchor
 
 uint64_t window_offsets_scratch_words(uint64_t num_reads) { return (num_reads + 1 + kScanTile - 1) / kScanTile + 1; }
 
-cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
-                                  uint64_t* block_sums, cudaStream_t stream) {
+cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_begins, const uint64_t* read_ends, uint64_t num_reads,
+                                  uint64_t* win_offsets, uint64_t* block_sums, cudaStream_t stream) {
     const uint64_t nblocks = (num_reads + 1 + kScanTile - 1) / kScanTile;
-    win_block_sums_kernel<<<(unsigned)nblocks, kBlock, 0, stream>>>(k, read_offsets, num_reads, block_sums);
+    win_block_sums_kernel<<<(unsigned)nblocks, kBlock, 0, stream>>>(k, read_begins, read_ends, num_reads, block_sums);
     win_scan_sums_kernel<<<1, kBlock, 0, stream>>>(block_sums, nblocks);
-    win_offsets_kernel<<<(unsigned)nblocks, kBlock, 0, stream>>>(k, read_offsets, num_reads, block_sums, win_offsets);
+    win_offsets_kernel<<<(unsigned)nblocks, kBlock, 0, stream>>>(k, read_begins, read_ends, num_reads, block_sums, win_offsets);
     g_launches.fetch_add(3);
     return cudaGetLastError();
 }
 
-cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
-                             const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
+cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_begins,
+                             const uint64_t* read_ends, const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
                              uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream) {
     if (num_reads == 0) return cudaSuccess;
     // 64-bit k-mers: streamed ids == window ids, so the window kernel writes the caller's buffer directly
@@ -997,8 +1072,8 @@ cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const 
     Anchor* an = static_cast<Anchor*>(anchors);
     if (an) {
         const int grid = grid_for(num_reads * kAnchorsPerRead, ctx.sm_count, 8);
-        cudaError_t e = ix.kmer_words == 1 ? launch(stream_anchor_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, num_reads, an)
-                                           : launch(stream_anchor_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, num_reads, an);
+        cudaError_t e = ix.kmer_words == 1 ? launch(stream_anchor_kernel<1>, grid, stream, ctx, ix, bases, read_begins, read_ends, num_reads, an)
+                                           : launch(stream_anchor_kernel<2>, grid, stream, ctx, ix, bases, read_begins, read_ends, num_reads, an);
         if (e != cudaSuccess) return e;
     }
     {
@@ -1008,10 +1083,10 @@ cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const 
         if (ez != cudaSuccess) return ez;
         cudaError_t e;
         if (ix.kmer_words == 1)
-            e = launch(stream_windows_kernel<1>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads,
+            e = launch(stream_windows_kernel<1>, grid, stream, ctx, ix, bases, read_begins, read_ends, win_offsets, num_reads,
                        (const Anchor*)an, win_id, win_aux, counters + 5);
         else
-            e = launch(stream_windows_kernel<2>, grid, stream, ctx, ix, bases, read_offsets, win_offsets, num_reads,
+            e = launch(stream_windows_kernel<2>, grid, stream, ctx, ix, bases, read_begins, read_ends, win_offsets, num_reads,
                        (const Anchor*)an, win_id, win_aux, counters + 5);
         if (e != cudaSuccess) return e;
     }
@@ -1020,8 +1095,29 @@ cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const 
         return launch(stream_classify_kernel, grid_for(total_windows_bound, ctx.sm_count, 8), stream, ctx, win_offsets, num_reads,
                       (const uint64_t*)win_id, (const uint64_t*)win_aux, counters);
     }
-    return launch(stream_scan_kernel<2>, grid_for(num_reads, ctx.sm_count, 8), stream, ctx, ix, bases, read_offsets, win_offsets,
-                  num_reads, win_id, win_aux, ids_out, counters);
+    return launch(stream_scan_kernel<2>, grid_for(num_reads, ctx.sm_count, 8), stream, ctx, ix, bases, read_begins, read_ends,
+                  win_offsets, num_reads, win_id, win_aux, ids_out, counters);
+}
+
+uint64_t parse_tiles(uint64_t n_bytes) { return (n_bytes + kParseTile - 1) / kParseTile; }
+
+cudaError_t launch_count_lines(const uint8_t* raw, uint64_t n_bytes, uint64_t* tile_counts, cudaStream_t stream) {
+    const uint64_t tiles = parse_tiles(n_bytes);
+    newline_count_kernel<<<(unsigned)tiles, kBlock, 0, stream>>>(raw, n_bytes, tile_counts);
+    // scan tiles + 1 entries (the caller zeroes the last one): entry [tiles] becomes the number of lines
+    win_scan_sums_kernel<<<1, kBlock, 0, stream>>>(tile_counts, tiles + 1);
+    g_launches.fetch_add(2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_read_spans(const uint8_t* raw, uint64_t n_bytes, const uint64_t* tile_offsets, uint64_t* line_start,
+                              uint64_t num_records, uint32_t lines_per_record, uint64_t* read_begins, uint64_t* read_ends,
+                              int sm_count, cudaStream_t stream) {
+    newline_positions_kernel<<<(unsigned)parse_tiles(n_bytes), kBlock, 0, stream>>>(raw, n_bytes, tile_offsets, line_start);
+    read_spans_kernel<<<grid_for(num_records, sm_count, 8), kBlock, 0, stream>>>(line_start, num_records, lines_per_record,
+                                                                                   read_begins, read_ends);
+    g_launches.fetch_add(2);
+    return cudaGetLastError();
 }
 
 }  // namespace sshash_b200

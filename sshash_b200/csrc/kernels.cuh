@@ -48,19 +48,32 @@ cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
 cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
                                       cudaStream_t stream);
 
-// win_offsets[r] = number of windows in reads [0, r), computed on the device from read_offsets
-cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_offsets, uint64_t num_reads, uint64_t* win_offsets,
-                                  uint64_t* block_sums, cudaStream_t stream);
+// Reads are spans of `bases`: read r = [read_begins[r], read_ends[r]) (contiguous reads:
+// read_offsets and read_offsets + 1).
+// win_offsets[r] = number of windows in reads [0, r), computed on the device from the spans
+cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_begins, const uint64_t* read_ends, uint64_t num_reads,
+                                  uint64_t* win_offsets, uint64_t* block_sums, cudaStream_t stream);
 uint64_t window_offsets_scratch_words(uint64_t num_reads);
 
 // Streaming membership over a batch of reads: per-window lookups, then the classification of the
 // windows into searches / extensions (one thread per window for 64-bit k-mers, the per-read replay
 // of the reference state machine for 128-bit ones).  total_windows_bound >= number of windows.
 // counters[5] += {num_kmers, searches, extensions, negative, invalid}.
-cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_offsets,
-                             const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
+cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_begins,
+                             const uint64_t* read_ends, const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
                              uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream);
 // scratch for the per-read alignment anchors (pass nullptr as `anchors` to look every window up)
 uint64_t streaming_anchor_bytes(uint64_t num_reads);
+
+// Device-side FASTA/FASTQ record parsing over a chunk of raw file bytes (16-byte padded buffer).
+//   launch_count_lines: tile_counts has parse_tiles(n) + 1 entries, the last one zeroed by the caller;
+//     on return entry [t] = newlines before tile t and entry [parse_tiles(n)] = number of newlines.
+//   launch_read_spans: line_start (lines + 1 entries) and the spans of the sequence lines of
+//     num_records records of lines_per_record lines each (FASTQ 4, FASTA 2).
+uint64_t parse_tiles(uint64_t n_bytes);
+cudaError_t launch_count_lines(const uint8_t* raw, uint64_t n_bytes, uint64_t* tile_counts, cudaStream_t stream);
+cudaError_t launch_read_spans(const uint8_t* raw, uint64_t n_bytes, const uint64_t* tile_offsets, uint64_t* line_start,
+                              uint64_t num_records, uint32_t lines_per_record, uint64_t* read_begins, uint64_t* read_ends,
+                              int sm_count, cudaStream_t stream);
 
 }  // namespace sshash_b200

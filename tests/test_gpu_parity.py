@@ -150,6 +150,74 @@ def test_streaming_device_buffers_and_file(dicts, name, tmp_path):
     assert d.streaming_query_from_file(str(tmp_path / "x.txt"))["num_kmers"] == 0  # unsupported extension
 
 
+def _set_env(**kv):
+    old = {k: os.environ.get(k) for k in kv}
+    for k, v in kv.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    return old
+
+
+@pytest.mark.parametrize("name", ["se_k31_m13", "se_k63_m8_canon"])
+def test_file_driver_device_side_record_parsing(dicts, name, tmp_path):
+    """FASTQ / FASTA records are found on the GPU (newline index over the raw file bytes).  Every
+    ragged shape the positional record structure of src/query.cpp:53-108 allows -- no final newline,
+    truncated last record, CRLF, empty and short sequence lines, '@'/'>' inside quality/sequence
+    lines -- with chunk sizes that cut records at every possible place, against the host line
+    parser (same library, SSHASH_GPU_HOST_PARSER=1) and against the unmodified reference."""
+    from oracle import ref
+    g, d = golden(name), dicts(name)
+    raw = g.z["read_bases"].tobytes().decode()
+    o = g.z["read_offsets"].astype(np.int64)
+    reads = [raw[o[i]:o[i + 1]] for i in range(min(len(o) - 1, 120))]
+    reads[3] = ""                                  # empty sequence line
+    reads[5] = reads[5][:10]                       # shorter than k
+    reads[7] = "".join(reads[20:40])               # one long read (several KB)
+    rd = ref.RefDictionary(g.index, max_k=g.max_k) if ref.available(g.max_k) else None
+    files = {}
+    fq = "".join("@r%d\n%s\n+\n%s\n" % (i, r, ("@>I" * len(r))[:len(r)]) for i, r in enumerate(reads))
+    files["a.fastq"] = fq
+    files["no_final_newline.fastq"] = fq[:-1]
+    files["truncated_after_seq.fastq"] = fq + "@last\n" + reads[1]
+    files["truncated_after_header.fastq"] = fq + "@last"
+    files["crlf.fastq"] = fq.replace("\n", "\r\n")
+    fa = "".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(reads))
+    files["a.fa"] = fa
+    files["no_final_newline.fasta"] = fa[:-1]
+    files["header_only_tail.fa"] = fa + ">last"
+    files["empty.fastq"] = ""
+    for fname, text in files.items():
+        path = tmp_path / fname
+        path.write_bytes(text.encode())
+        old = _set_env(SSHASH_GPU_HOST_PARSER=1)
+        want = d.streaming_query_from_file(str(path))
+        _set_env(**old)
+        if rd is not None:
+            refrep, _ = rd.streaming_file(str(path))
+            assert [want[k] for k in REPORT_KEYS] == [refrep[k] for k in REPORT_KEYS], fname
+        for chunk in (None, 64, 257, 1000, 4096, 65536):   # 64/257/1000 < the long read: host-parser fallback for that record
+            old = _set_env(SSHASH_GPU_FILE_CHUNK=chunk)
+            got = d.streaming_query_from_file(str(path))
+            _set_env(**old)
+            assert got == want, (fname, chunk)
+    if rd is not None:
+        rd.close()
+    # gzip input goes through the same device parser
+    import gzip
+    gz = tmp_path / "reads.fq.gz"
+    with gzip.open(gz, "wt") as f:
+        f.write(fq)
+    old = _set_env(SSHASH_GPU_FILE_CHUNK=3000)
+    got = d.streaming_query_from_file(str(gz))
+    _set_env(**old)
+    old = _set_env(SSHASH_GPU_HOST_PARSER=1)
+    want = d.streaming_query_from_file(str(tmp_path / "a.fastq"))
+    _set_env(**old)
+    assert got == want and got["num_kmers"] > 0
+
+
 @pytest.mark.parametrize("name", ["se_k31_m13", "sal100_k31_m11_canon", "se_k63_m21"])
 def test_streaming_multiline_fasta_vs_reference(dicts, name, tmp_path):
     """streaming_query_from_fasta_file_multiline (src/query.cpp:9-51): all lines of a run -- header

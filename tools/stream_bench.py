@@ -51,7 +51,7 @@ def make_reads(d, n_reads, read_len=150, seed=42, device="cuda"):
     return reads.reshape(-1), offsets
 
 
-def run(index, n_reads, steps=3, max_k=0, check=True):
+def run(index, n_reads, steps=3, max_k=0, check=True, files=False):
     import torch
     import sshash_b200
     d = sshash_b200.Dictionary(index, max_k=max_k)
@@ -92,8 +92,69 @@ def run(index, n_reads, steps=3, max_k=0, check=True):
         gids, grep = d.streaming_batch(hbn[: m * 150], ho[: m + 1])
         assert (gids == oids).all() and grep == orep, "streaming differs from the oracle"
         res["checked_reads_vs_oracle"] = m
+    if files:
+        res["file"] = file_leg(d, index, hbn, n_reads, max_k)
     d.close()
     return res
+
+
+def file_leg(d, index, hbn, n_reads, max_k, read_len=150):
+    """dictionary::streaming_query_from_file on an uncompressed FASTQ file (4 lines per read), the
+    reference's own streaming protocol (tools/query.cpp): records parsed on the GPU vs the host
+    line parser of the same library vs the unmodified reference (single thread, as published)."""
+    import tempfile
+    reads = hbn.reshape(n_reads, read_len)
+    wd = tempfile.mkdtemp(prefix="sshash_fq_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = {}
+
+    def write(path, m):
+        hdr = np.frombuffer(b"@read:0123456789\n", dtype=np.uint8)
+        rec = np.empty((m, hdr.size + read_len + 3 + read_len + 1), dtype=np.uint8)
+        rec[:, :hdr.size] = hdr
+        rec[:, hdr.size:hdr.size + read_len] = reads[:m]
+        rec[:, hdr.size + read_len:hdr.size + read_len + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+        rec[:, hdr.size + read_len + 3:-1] = ord("I")
+        rec[:, -1] = ord("\n")
+        rec.tofile(path)
+        return rec.size
+
+    fq = os.path.join(wd, "reads.fastq")
+    nbytes = write(fq, n_reads)
+    nwin = n_reads * (read_len - d.k() + 1)
+    out["file_bytes"] = nbytes
+    for name, env in (("device_parser", None), ("host_parser", "1")):
+        if env is None:
+            os.environ.pop("SSHASH_GPU_HOST_PARSER", None)
+        else:
+            os.environ["SSHASH_GPU_HOST_PARSER"] = env
+        rep = d.streaming_query_from_file(fq)      # warm-up (page cache, workspace)
+        t0 = time.perf_counter()
+        rep = d.streaming_query_from_file(fq)
+        dt = time.perf_counter() - t0
+        out[name] = {"ms": dt * 1e3, "windows_per_s": nwin / dt, "file_GB_per_s": nbytes / dt / 1e9}
+        out[name + "_report"] = rep
+    os.environ.pop("SSHASH_GPU_HOST_PARSER", None)
+    assert out["device_parser_report"] == out["host_parser_report"]
+    del out["host_parser_report"]
+    os.remove(fq)
+    from oracle import ref
+    mk = max_k or (31 if d.k() <= 31 else 63)
+    if ref.available(mk):
+        m = min(n_reads, 100000)
+        small = os.path.join(wd, "sample.fastq")
+        write(small, m)
+        os.environ.pop("SSHASH_GPU_HOST_PARSER", None)
+        got = d.streaming_query_from_file(small)
+        rd = ref.RefDictionary(index, max_k=mk)
+        t0 = time.perf_counter()
+        want, _ = rd.streaming_file(small)
+        dt = time.perf_counter() - t0
+        rd.close()
+        assert all(got[k] == want[k] for k in got), (got, want)
+        out["reference_1thread"] = {"reads": m, "windows_per_s": m * (read_len - d.k() + 1) / dt, "checked": True}
+        os.remove(small)
+    os.rmdir(wd)
+    return out
 
 
 if __name__ == "__main__":
@@ -101,5 +162,6 @@ if __name__ == "__main__":
     ap.add_argument("--index", default=os.path.join(ROOT, "tests", "golden", "se_k31_m13.sshash"))
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--max-k", type=int, default=0)
+    ap.add_argument("--files", action="store_true", help="also time streaming_query_from_file on a FASTQ file")
     a = ap.parse_args()
-    print(json.dumps(run(a.index, a.reads, max_k=a.max_k)))
+    print(json.dumps(run(a.index, a.reads, max_k=a.max_k, files=a.files)))
