@@ -352,7 +352,7 @@ template <int W, bool SMALL_M>
 __device__ __forceinline__ Minimizer compute_minimizer_fast(const DeviceIndex& ix, Kmer<W> x) {
     const uint32_t k = ix.k, m = ix.m;
     const uint32_t n = k - m + 1;                      // <= 63
-    const uint32_t mm = SMALL_M ? (uint32_t)low_mask(2 * m) : (uint32_t)low_mask(2 * m - 32);
+    const uint32_t mm = SMALL_M ? (uint32_t)ix.mmer_mask : (uint32_t)(ix.mmer_mask >> 32);
     uint32_t r[4];
     kmer_words32(x, r);
     uint32_t left = 0xffffffffu, right = 0xffffffffu;   // keys over global positions
@@ -381,7 +381,7 @@ __device__ __forceinline__ Minimizer compute_minimizer_fast(const DeviceIndex& i
 #undef SSHASH_STEP
     const uint32_t pos = left & 63u;
     if (pos != 63u - (right & 63u)) return compute_minimizer_exact<SMALL_M>(x, k, m, ix.magic);
-    return {kmer_bits_at(x, 2 * pos) & low_mask(2 * m), pos};
+    return {kmer_bits_at(x, 2 * pos) & ix.mmer_mask, pos};
 }
 
 template <int W>
