@@ -211,12 +211,15 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         first_part.push_back(parts.size());
         for (size_t i = 0; i != p->parts.size(); ++i) {
             auto const& sp = p->parts[i];
-            if (sp.num_keys >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: MPHF partition with >= 2^32 keys");
+            if ((sp.num_keys | sp.table_size | sp.num_buckets) >> 32)
+                return fail(SSHASH_GPU_EFORMAT, "unsupported index: MPHF partition with >= 2^32 keys / slots / buckets");
+            if ((word | free_pool.size()) >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: MPHF pools exceed 2^32 entries");
+            if (sp.pilots.width > 64 || sp.table_size < sp.num_keys) return fail(SSHASH_GPU_EFORMAT, "malformed index file (MPHF partition)");
             DevPhfPart o{};
             o.offset = p->offsets[i];
-            o.num_keys = sp.num_keys; o.table_size = sp.table_size; o.num_buckets = sp.num_buckets;
-            o.pilots_word = word; o.pilot_mask = sp.pilots.mask; o.pilot_width = (uint32_t)sp.pilots.width;
-            o.free_off = free_pool.size();
+            o.num_keys = (uint32_t)sp.num_keys; o.table_size = (uint32_t)sp.table_size; o.num_buckets = (uint32_t)sp.num_buckets;
+            o.pilots_word = (uint32_t)word; o.pilot_width = (uint32_t)sp.pilots.width;
+            o.free_off = (uint32_t)free_pool.size();
             if (sp.pilots.data.n) std::memcpy(pilots_host.data() + word, f.ptr(sp.pilots.data), sp.pilots.data.bytes());
             word += sp.pilots.data.n;
             const uint64_t n_free = sp.table_size - sp.num_keys;
@@ -364,9 +367,6 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     }
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
     d->info.device_bytes = up.bytes;
-    // SSHASH_GPU_SPECULATE=0/1 forces the choice (measurements); default: indexes that do not fit L2
-    if (const char* e = std::getenv("SSHASH_GPU_SPECULATE")) ix.speculate_locate = e[0] == '1';
-    else ix.speculate_locate = up.bytes > (96ull << 20);
     return SSHASH_GPU_OK;
 }
 

@@ -42,16 +42,14 @@ struct DevCompact {            // bits::compact_vector read side, compact_vector
     uint32_t pad_;
 };
 
-struct DevPhfPart {            // one pthash::single_phf (single_phf.hpp:116-142) + its offset
+struct DevPhfPart {            // one pthash::single_phf (single_phf.hpp:116-142) + its offset: 32 bytes, two 128-bit loads
     uint64_t offset;           // partitioned_phf::partition::offset, partitioned_phf.hpp:20-38
-    uint64_t num_keys;
-    uint64_t table_size;
-    uint64_t num_buckets;
-    uint64_t pilots_word;      // first word of this partition's pilots inside the pilots pool
-    uint64_t pilot_mask;
-    uint64_t free_off;         // first free slot of this partition inside the free-slot pool
+    uint32_t pilots_word;      // first word of this partition's pilots inside the pilots pool
+    uint32_t free_off;         // first free slot of this partition inside the free-slot pool
+    uint32_t num_keys;         // the three sizes are < 2^32 per partition (checked at open time), which
+    uint32_t table_size;       // turns the 64x64-bit high multiplies of the bucketer / of fastmod-free
+    uint32_t num_buckets;      // `position` into 64x32-bit ones
     uint32_t pilot_width;
-    uint32_t pad_;
 };
 
 struct DevPhf {                // pthash::partitioned_phf, partitioned_phf.hpp:139-149
@@ -102,12 +100,6 @@ struct DeviceIndex {
     uint32_t mini_left[16], mini_right[16];
     uint64_t kmer_mask_lo, kmer_mask_hi;   // low 2k bits set (second word: bits 64..2k-1)
     uint64_t mmer_mask;                    // low 2m bits set
-    // 1 = launch the lookup kernels that issue the end-point probe of the first candidate next to its
-    // k-mer read (lookup_regular_with<SPEC>).  Pays when `strings` lives in HBM (+3.5 % on a
-    // 5e8-k-mer index), costs 2.5 % when the whole index is L2-resident and the kernel is
-    // issue-bound; set at open time from the index size (host-side dispatch only).
-    uint32_t speculate_locate;
-    uint32_t pad2_;
 };
 
 #ifdef __CUDACC__
@@ -427,17 +419,26 @@ __device__ __forceinline__ Hash128 city_hash_u128(const DevPhf& f, uint64_t lo, 
 // (single_phf.hpp:68-78) with opt_bucketer::bucket (utils/bucketers.hpp:38-39), range_bucketer
 // (:129-131), compact pilots (utils/encoders.hpp:33-35), mix (utils/hasher.hpp:41-43) and the
 // minimal remap through the (decoded) free slots.
+// (x * y) >> 64 for a 32-bit y
+__device__ __forceinline__ uint32_t mulhi_64x32(uint64_t x, uint32_t y) {
+    const uint64_t lo = (uint64_t)(uint32_t)x * y;
+    return (uint32_t)(((x >> 32) * y + (lo >> 32)) >> 32);
+}
+
 __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const DevPhf& f, Hash128 h) {
     uint64_t part = 0;
     if (f.num_partitions > 1) part = (((h.first ^ h.second) >> 32) * f.num_partitions) >> 32;
-    const DevPhfPart* __restrict__ p = f.parts + part;
+    const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(f.parts + part);
+    const uint4 a = __ldg(rec), b = __ldg(rec + 1);
+    const uint64_t offset = ((uint64_t)a.y << 32) | a.x;
+    const uint32_t pilots_word = a.z, free_off = a.w, num_keys = b.x, table_size = b.y, num_buckets = b.z, pilot_width = b.w;
     const uint64_t h1 = h.first;
-    uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
-    uint64_t bucket = __umul64hi(H, p->num_buckets);
-    uint64_t pilot = compact_get<true>(ix.pilots + p->pilots_word, p->pilot_width, p->pilot_mask, bucket);
-    uint64_t pos = __umul64hi((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, p->table_size);
-    if (pos >= p->num_keys) pos = ld32<true>(ix.free_slots + p->free_off + (pos - p->num_keys));
-    return p->offset + pos;
+    const uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
+    const uint32_t bucket = mulhi_64x32(H, num_buckets);
+    const uint64_t pilot = compact_get<true>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket);
+    uint32_t pos = mulhi_64x32((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, table_size);
+    if (pos >= num_keys) pos = ld32<true>(ix.free_slots + free_off + (pos - num_keys));
+    return offset + pos;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -454,23 +455,6 @@ __device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_
     begin = cur; end = next;
     return i;
 }
-// The same in two halves, so that the directory and end-point loads of the FIRST candidate (the only
-// one in a singleton bucket) are in flight together with the cold read of its k-mer from `strings`
-// instead of starting after the comparison: two L2 round trips off the dependent chain.
-struct LocateProbe { uint64_t i, cur, next; };
-__device__ __forceinline__ LocateProbe locate_begin(const DeviceIndex& ix, uint64_t x) {
-    LocateProbe p;
-    p.i = ld32<true>(ix.ends_dir + (x >> ix.dir_shift));
-    p.cur = ld64<true>(ix.ends + p.i);
-    p.next = ld64<true>(ix.ends + p.i + 1);
-    return p;
-}
-__device__ __forceinline__ uint64_t locate_finish(const DeviceIndex& ix, LocateProbe p, uint64_t x, uint64_t& begin, uint64_t& end) {
-    while (p.next <= x) { p.cur = p.next; ++p.i; p.next = ld64<true>(ix.ends + p.i + 1); }
-    begin = p.cur; end = p.next;
-    return p.i;
-}
-
 // ------------------------------------------------------------------------------------------------
 // one lookup
 // ------------------------------------------------------------------------------------------------
@@ -511,7 +495,9 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
     uint32_t fp = 0;
     if (USE_FP) fp = minimizer_fingerprint(ix, minimizer);   // before the loads: only 32 bits stay live across them
     uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
-    uint64_t code = compact_get<false>(ix.codewords, id);
+    // entries are exactly 32 bits wide whenever the reference's codeword has <= 24 bits (api.cu)
+    uint64_t code = ix.codewords.width == 32 ? (uint64_t)ld32<false>(reinterpret_cast<const uint32_t*>(ix.codewords.data) + id)
+                                             : compact_get<false>(ix.codewords, id);
     heavy = false;
     if (ix.cw_fp_bits) {
         if (USE_FP && (uint32_t)(code >> ix.cw_code_bits) != fp) return 0;
@@ -545,7 +531,7 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
 // FULL = also produce minimizer_found exactly (needs the m-mer check of spss.hpp:46-65); without
 // it the k-mer comparison alone decides, which yields the same ids (a k-mer match implies the
 // m-mer match because the minimizer is a substring of the k-mer at pos_in_kmer).
-template <int W, bool FULL, bool SPEC = false>
+template <int W, bool FULL>
 __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<W> x, Minimizer mi, LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     uint64_t first; bool heavy;
@@ -558,30 +544,20 @@ __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<
     // The candidate scan only COMPARES; the string is located once, after the scan, so that the
     // lanes of a warp (most have a single candidate, a few a long mid-load bucket) reconverge
     // before the end-point loads instead of each running them inside its own divergent iteration.
-    // SPEC: the end-point probe of the first candidate is issued speculatively, next to its k-mer read.
-    LocateProbe probe{0, 0, 0};
-    Kmer<W> r0 = x;
-    const bool v0 = off0 >= mi.pos;
-    if (SPEC && v0) {
-        r0 = read_kmer(ix, off0 - mi.pos, (Kmer<W>*)nullptr);
-        probe = locate_begin(ix, off0 - mi.pos);
-    }
+    // (Issuing the end-point probe of the first candidate speculatively, next to its k-mer read,
+    // was measured too: +-0.5 % on a 5e8-k-mer index, -2.5 % on an L2-resident one: not kept.)
     for (uint32_t i = 0;; ++i) {
         uint64_t ko = 0;
         bool hit = false;
-        if (SPEC && i == 0 && v0 && kmer_eq(r0, x)) { ko = off0 - mi.pos; hit = true; }
-        else {
-            if (SPEC && i == 0) i = 1;
-            for (; i < n; ++i) {
-                uint64_t off = (!SPEC && i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
-                if (off < mi.pos) continue;
-                ko = off - mi.pos;
-                if (kmer_eq(read_kmer(ix, ko, (Kmer<W>*)nullptr), x)) { hit = true; break; }
-            }
+        for (; i < n; ++i) {
+            uint64_t off = (i == 0) ? off0 : compact_get<false>(ix.mid_load, first + i);
+            if (off < mi.pos) continue;
+            ko = off - mi.pos;
+            if (kmer_eq(read_kmer(ix, ko, (Kmer<W>*)nullptr), x)) { hit = true; break; }
         }
         if (!hit) break;
         uint64_t sb, se;
-        uint64_t sid = (SPEC && i == 0) ? locate_finish(ix, probe, ko, sb, se) : locate_string(ix, ko, sb, se);
+        uint64_t sid = locate_string(ix, ko, sb, se);
         if (ko < se - k + 1) {                          // spss.hpp:233: reject k-mers spanning two strings
             res.kmer_id = ko - sid * (k - 1);
             res.kmer_id_in_string = ko - sb;
@@ -596,9 +572,9 @@ __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<
     return false;
 }
 
-template <int W, bool FULL, bool SPEC = false>
+template <int W, bool FULL>
 __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x, LookupResult& res) {
-    return lookup_regular_with<W, FULL, SPEC>(ix, x, compute_minimizer(ix, x), res);
+    return lookup_regular_with<W, FULL>(ix, x, compute_minimizer(ix, x), res);
 }
 
 // Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)

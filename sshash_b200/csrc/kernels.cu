@@ -108,7 +108,7 @@ template <> struct RcQueue<2> {
 // 32 are parked (or the input is exhausted), 32 parked reverse complements.  CANON selects the
 // canonical (src/dictionary.cpp:24-56) or the regular (:7-22, :64-78) flow at compile time so that
 // each instantiation carries only its own path.
-template <int W, int MODE, bool ASCII, bool CANON, int MINB, bool SPEC = false>
+template <int W, int MODE, bool ASCII, bool CANON, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
               uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
@@ -147,7 +147,7 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
         LookupResult r;
         if (active) {
             if (CANON) found = lookup_canonical<W, FULL>(ix, x, r);
-            else found = lookup_regular<W, FULL, SPEC>(ix, x, r);
+            else found = lookup_regular<W, FULL>(ix, x, r);
         }
         const bool park = active && fresh && two_pass && !found;
         if (active && !park) {
@@ -995,10 +995,7 @@ cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const voi
                        : launch(lookup_kernel<W, MODE, ASCII, false, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
 #define SSHASH_DISPATCH_MODE(W, ASCII)                     \
     do {                                                   \
-        if (mode == 0 && !ix.canonical && ix.speculate_locate)                                                          \
-            err = launch(lookup_kernel<W, 0, ASCII, false, kLookupMinBlocks, true>, grid, stream, ctx, ix, queries, n, crc, \
-                         ids, full, member);                                                                            \
-        else if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);    \
+        if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);         \
         else if (mode == 1) SSHASH_LAUNCH(W, 1, ASCII);    \
         else SSHASH_LAUNCH(W, 2, ASCII);                   \
     } while (0)

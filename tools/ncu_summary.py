@@ -6,6 +6,7 @@ committed under profiles/.
     python tools/ncu_summary.py launches gpurun_out/launches.csv > profiles/rNN_launches.txt
 """
 import csv
+import re
 import subprocess
 import sys
 
@@ -65,6 +66,18 @@ def launches(path):
     for n in order:
         v = agg[n]
         print("%-72s %6d %12.1f %12.3f %6.1f%%" % (n, len(v), sum(v) / len(v) / 1e3, sum(v) / 1e6, 100 * sum(v) / tot))
+    # the launches of this library one by one, in order (a bench step = one full-batch lookup_kernel
+    # launch; the short lookup_kernel launches are the 4 Mi-query chunks of the host-buffer pipeline)
+    print()
+    print("launches of sshash_b200 kernels >= 1 ms, in order (ms):")
+    line = []
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi or "sshash_b200" not in r[ki]:
+            continue
+        v = float(r[vi].replace(",", "")) / 1e6
+        if v >= 1.0:
+            line.append("%s [grid %s] %.3f" % (re.search(r"(\w+_kernel)", r[ki]).group(1), r[gi].strip("()").split(",")[0], v))
+    print("  " + "\n  ".join(line))
 
 
 if __name__ == "__main__":
