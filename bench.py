@@ -18,7 +18,8 @@ tools/perf.hpp:41-51).  One step = one pass of the lookup path over the whole 1e
 --impl reference times the reference's CPU implementation (oracle/_ref when built, else the C
 oracle port) with all host threads on a bounded sample of the same workload.
 With N > 1 (torchrun) every rank holds a replica of the index and its own 1e8-query shard (weak
-scaling, no data-path collective); the NCCL gather of the ids to rank 0 is timed separately.
+scaling, no data-path collective); the gather of the ids to rank 0 is timed separately (`gather`):
+fused into the lookup kernels as NVLink peer stores, and as NCCL send/recv for comparison.
 """
 from __future__ import annotations
 
@@ -341,27 +342,36 @@ def main():
     e2e_value = world * n * args.steps / e2e_s
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- NCCL gather of the ids to rank 0 (the only collective of the sharded design), timed apart:
-    # sshash_b200.sharded.ShardedLookup = shard lookup + chunked p2p gather overlapped with the kernels
+    # ---- gather of the ids to rank 0 (the only communication of the sharded design), timed apart.
+    # sshash_b200.sharded.ShardedLookup: "peer" = every rank's lookup kernel stores its ids straight into
+    # rank 0's vector through NVLink peer stores (the gather is fused into the lookup kernel);
+    # "p2p" = ids written locally + chunked NCCL send/recv, kept for comparison.
     gather = None
     if world > 1:
         from sshash_b200.sharded import ShardedLookup
-        sl = ShardedLookup.for_dictionary(d, chunk_queries=1 << 24)
-        for _ in range(2):
-            sl.lookup(kmers, dst=0)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        local_ids, gathered = sl.lookup(kmers, dst=0)
-        g1.record()
-        barrier()
-        assert torch.equal(local_ids, ids)
-        if rank == 0:
-            assert torch.equal(gathered[:n], ids)
-        gt = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather = {"lookup_plus_gather_ms": float(gt.item()), "bytes_to_rank0": (world - 1) * n * 8,
-                  "lookups_per_s_with_gather": world * n / (float(gt.item()) * 1e-3)}
+        gather = {"bytes_to_rank0": (world - 1) * n * 8}
+        for mode in ("peer", "p2p"):
+            sl = ShardedLookup.for_dictionary(d, chunk_queries=1 << 24, mode=mode)
+            for _ in range(3):
+                sl.lookup(kmers, dst=0)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                local_ids, gathered = sl.lookup(kmers, dst=0)
+            g1.record()
+            barrier()
+            assert torch.equal(local_ids, ids)
+            if rank == 0:
+                assert torch.equal(gathered[:n], ids)
+            gt = torch.tensor([g0.elapsed_time(g1) / 3], device=dev, dtype=torch.float64)
+            dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+            gather[mode] = {"lookup_plus_gather_ms": float(gt.item()),
+                            "lookups_per_s_with_gather": world * n / (float(gt.item()) * 1e-3)}
+            del sl, gathered, local_ids
+        gather["mode"] = "peer: ids stored by the lookup kernels straight into rank 0's vector over NVLink (symmetric memory)"
+        gather["lookup_plus_gather_ms"] = gather["peer"]["lookup_plus_gather_ms"]
+        gather["lookups_per_s_with_gather"] = gather["peer"]["lookups_per_s_with_gather"]
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -3,9 +3,19 @@
 Lookups are independent and read-only against a static index that fits one GPU, so the path shards
 by QUERY: every rank (one process per GPU, torch.distributed) holds a replica of the index, looks
 up its own contiguous slice of the batch, and the only communication is the gather of the
-resulting ids -- there is no exchange step inside the algorithm.  The gather is chunked and
-overlapped with the lookup kernel of the next chunk (NCCL over NVLink on GPUs; gloo in the CPU
-tests, where the lookup function is injected).
+resulting ids -- there is no exchange step inside the algorithm.  Two gather modes:
+
+  "peer"  (GPUs of one NVLink/NVSwitch box) the gather is FUSED into the lookup kernel: rank dst owns
+          the gathered vector in symmetric memory (torch.distributed._symmetric_memory), every rank
+          maps it, and each rank's lookup kernel stores its ids straight into its slice of that
+          vector through NVLink peer stores (the C ABI takes any device pointer as `kmer_ids`).  No
+          gather kernel, no staging copy, no SMs taken from the lookups; a device-side barrier on
+          the stream publishes the result.  Measured at N=2 on cfg2: 4.72 ms per 2x1e8 lookups with
+          the ids gathered vs 4.72 ms without (tools/micro/peer_gather.py).
+  "p2p"   chunked isend/irecv of locally written ids, overlapped with the next chunk's lookup
+          kernel (NCCL on GPUs; gloo in the CPU tests, where the lookup function is injected).  An
+          NCCL send kernel needs SMs the persistent lookup CTAs hold, so this mode costs the full
+          transfer time on top of the lookups (+2.1 ms per GB at N=2).
 """
 from __future__ import annotations
 
@@ -27,29 +37,66 @@ def shard_sizes(n: int, world: int) -> List[int]:
 class ShardedLookup:
     """lookup_fn(kmers_chunk) -> ids_chunk runs on this rank's device (Dictionary.lookup_batch)."""
 
-    def __init__(self, lookup_fn: Callable, words: int = 1, group=None, chunk_queries: int = 1 << 25):
+    def __init__(self, lookup_fn: Callable, words: int = 1, group=None, chunk_queries: int = 1 << 25,
+                 lookup_into: Optional[Callable] = None, mode: str = "p2p"):
         import torch.distributed as dist
         self.dist = dist
         self.lookup_fn = lookup_fn
+        self.lookup_into = lookup_into       # lookup_into(kmers, out): ids written into `out` (any device pointer)
         self.words = words
         self.group = group
         self.chunk = int(chunk_queries)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        if mode not in ("p2p", "peer"):
+            raise ValueError("mode must be 'p2p' or 'peer'")
+        if mode == "peer" and lookup_into is None:
+            raise ValueError("mode 'peer' needs lookup_into")
+        self.mode = mode
+        self._symm = None                    # (buffer, handle, capacity, dst)
 
     @classmethod
-    def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25):
+    def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25, mode: str = "auto"):
+        """mode "auto": peer stores when the process group runs on NCCL (GPUs of one box), else p2p."""
+        import torch.distributed as dist
+        if mode == "auto":
+            mode = "peer" if (dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1) else "p2p"
         return cls(lambda k: dictionary.lookup_batch(k), words=dictionary.words, group=group,
-                   chunk_queries=chunk_queries)
+                   chunk_queries=chunk_queries, lookup_into=lambda k, out: dictionary.lookup_batch(k, out=out), mode=mode)
+
+    def _gathered_buffer(self, total: int, dst: int, device):
+        """Symmetric buffer of >= total ids: (this rank's allocation, view of rank dst's allocation)."""
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        if self._symm is None or self._symm[2] < total or self._symm[3] != dst:
+            cap = int(total)
+            buf = symm_mem.empty(cap, dtype=torch.int64, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
+            self._symm = (buf, hdl, cap, dst)
+        buf, hdl, cap, _ = self._symm
+        return buf, hdl, hdl.get_buffer(dst, (cap,), torch.int64)
+
+    def _lookup_peer(self, local_kmers, dst: int, sizes, starts):
+        n_local = sizes[self.rank]
+        buf, hdl, remote = self._gathered_buffer(sum(sizes), dst, local_kmers.device)
+        mine = remote[starts[self.rank]:starts[self.rank] + n_local]
+        hdl.barrier()                                    # rank dst has consumed the previous result (stream order)
+        if n_local:
+            self.lookup_into(local_kmers, mine)          # ids go over NVLink into rank dst's vector
+        hdl.barrier()                                    # on the current stream: every rank's stores are done
+        return mine, (buf[:sum(sizes)] if self.rank == dst else None)
 
     def lookup(self, local_kmers, dst: Optional[int] = 0):
         """Look up this rank's shard.  Returns (local_ids, gathered) where `gathered` is, on rank
         `dst`, the ids of ALL ranks concatenated in rank order (= global query order for shards made
-        with shard_range); None elsewhere, or everywhere when dst is None."""
+        with shard_range); None elsewhere, or everywhere when dst is None.  In "peer" mode local_ids
+        is this rank's slice of rank dst's vector (peer-mapped memory) and both results are valid
+        until the next call."""
         import torch
         dist = self.dist
         n_local = local_kmers.numel() // self.words
-        local_ids = torch.empty(n_local, dtype=torch.int64, device=local_kmers.device)
+        if dst is None or self.world == 1 or self.mode != "peer":
+            local_ids = torch.empty(n_local, dtype=torch.int64, device=local_kmers.device)
         if dst is None or self.world == 1:
             for lo in range(0, n_local, self.chunk):
                 hi = min(n_local, lo + self.chunk)
@@ -61,6 +108,8 @@ class ShardedLookup:
                         group=self.group)
         sizes = [int(s.item()) for s in sizes_t]
         starts = [sum(sizes[:r]) for r in range(self.world)]
+        if self.mode == "peer":
+            return self._lookup_peer(local_kmers, dst, sizes, starts)
         gathered = None
         pending = []
         if self.rank == dst:

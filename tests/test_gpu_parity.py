@@ -409,3 +409,24 @@ def test_multi_partition_index_vs_oracle(tmp_path):
     for f in full.dtype.names:
         assert (full[f] == fa_[f]).all(), f
     d.close()
+
+
+def test_sharded_lookup_with_peer_store_gather_two_gpus():
+    """N > 1: every rank's lookup kernel stores its ids straight into rank 0's gathered vector through
+    NVLink peer stores (sshash_b200.sharded, mode "peer"); rank 0 checks every slice against the
+    owner's sampled ids.  Needs two GPUs on the box (the CPU suite covers the host logic with gloo)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "micro", "peer_gather.py"),
+           os.path.join(root, "tests", "golden", "se_k31_m13.sshash"), "3000000"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    assert r["world"] == 2 and r["peer_ms"] > 0
