@@ -12,6 +12,11 @@ resulting ids -- there is no exchange step inside the algorithm.  Two gather mod
           gather kernel, no staging copy, no SMs taken from the lookups; a device-side barrier on
           the stream publishes the result.  Measured at N=2 on cfg2: 4.72 ms per 2x1e8 lookups with
           the ids gathered vs 4.72 ms without (tools/micro/peer_gather.py).
+  "copy"  ids written locally chunk by chunk, each finished chunk pushed into rank dst's symmetric
+          vector by a device-to-device memcpy on a side stream (copy engines over NVLink) while the
+          next chunk is looked up.  For many senders: the 8-byte stores of "peer" mode that come out
+          of the reverse-complement queue are scattered, and 7 ranks of them fill rank 0's NVLink
+          ingress at ~300 GB/s, whereas the copy engines move full-size packets.
   "p2p"   chunked isend/irecv of locally written ids, overlapped with the next chunk's lookup
           kernel (NCCL on GPUs; gloo in the CPU tests, where the lookup function is injected).  An
           NCCL send kernel needs SMs the persistent lookup CTAs hold, so this mode costs the full
@@ -48,12 +53,13 @@ class ShardedLookup:
         self.chunk = int(chunk_queries)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        if mode not in ("p2p", "peer"):
-            raise ValueError("mode must be 'p2p' or 'peer'")
-        if mode == "peer" and lookup_into is None:
-            raise ValueError("mode 'peer' needs lookup_into")
+        if mode not in ("p2p", "peer", "copy"):
+            raise ValueError("mode must be 'p2p', 'peer' or 'copy'")
+        if mode in ("peer", "copy") and lookup_into is None:
+            raise ValueError("mode '%s' needs lookup_into" % mode)
         self.mode = mode
         self._symm = None                    # (buffer, handle, capacity, dst)
+        self._side = None                    # copy stream of mode "copy"
 
     @classmethod
     def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25, mode: str = "auto"):
@@ -86,6 +92,36 @@ class ShardedLookup:
         hdl.barrier()                                    # on the current stream: every rank's stores are done
         return mine, (buf[:sum(sizes)] if self.rank == dst else None)
 
+    def _lookup_copy(self, local_kmers, dst: int, sizes, starts):
+        """ids written locally chunk by chunk; each finished chunk is pushed into rank dst's vector by a
+        device-to-device memcpy on a side stream (copy engines over NVLink: no SMs, full-size packets)
+        while the next chunk's lookup kernel runs."""
+        import torch
+        n_local = sizes[self.rank]
+        buf, hdl, remote = self._gathered_buffer(sum(sizes), dst, local_kmers.device)
+        mine = remote[starts[self.rank]:starts[self.rank] + n_local]
+        hdl.barrier()
+        if self.rank == dst:                             # the root's slice is local memory: look up in place
+            if n_local:
+                self.lookup_into(local_kmers, mine)
+            local_ids = mine
+        else:
+            local_ids = torch.empty(n_local, dtype=torch.int64, device=local_kmers.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=local_kmers.device)
+            main = torch.cuda.current_stream(local_kmers.device)
+            for lo in range(0, n_local, self.chunk):
+                hi = min(n_local, lo + self.chunk)
+                self.lookup_into(local_kmers[lo * self.words:hi * self.words], local_ids[lo:hi])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._side.wait_event(ev)
+                with torch.cuda.stream(self._side):
+                    mine[lo:hi].copy_(local_ids[lo:hi], non_blocking=True)
+            main.wait_stream(self._side)
+        hdl.barrier()
+        return local_ids, (buf[:sum(sizes)] if self.rank == dst else None)
+
     def lookup(self, local_kmers, dst: Optional[int] = 0):
         """Look up this rank's shard.  Returns (local_ids, gathered) where `gathered` is, on rank
         `dst`, the ids of ALL ranks concatenated in rank order (= global query order for shards made
@@ -95,7 +131,7 @@ class ShardedLookup:
         import torch
         dist = self.dist
         n_local = local_kmers.numel() // self.words
-        if dst is None or self.world == 1 or self.mode != "peer":
+        if dst is None or self.world == 1 or self.mode == "p2p":
             local_ids = torch.empty(n_local, dtype=torch.int64, device=local_kmers.device)
         if dst is None or self.world == 1:
             for lo in range(0, n_local, self.chunk):
@@ -110,6 +146,8 @@ class ShardedLookup:
         starts = [sum(sizes[:r]) for r in range(self.world)]
         if self.mode == "peer":
             return self._lookup_peer(local_kmers, dst, sizes, starts)
+        if self.mode == "copy":
+            return self._lookup_copy(local_kmers, dst, sizes, starts)
         gathered = None
         pending = []
         if self.rank == dst:

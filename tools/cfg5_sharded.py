@@ -44,7 +44,7 @@ def main():
     ap.add_argument("--batch", type=int, default=125_000_000)
     ap.add_argument("--oracle-sample", type=int, default=1_000_000)
     ap.add_argument("--chunk", type=int, default=1 << 25, help="p2p mode: queries per lookup launch / per send of the gather")
-    ap.add_argument("--mode", default="auto", choices=["auto", "peer", "p2p"],
+    ap.add_argument("--mode", default="auto", choices=["auto", "peer", "copy", "p2p"],
                     help="gather: ids stored straight into rank 0's vector over NVLink (peer) or NCCL send/recv (p2p)")
     a = ap.parse_args()
 
@@ -96,6 +96,7 @@ def main():
     found_neg = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     oracle_checked = 0
+    rc_twins = 0
     for b in range(n_batches + 1):                      # batch 0 is the warm-up
         ids = torch.randint(0, nk, (B // 2,), generator=gen, device=dev, dtype=torch.int64)
         q = torch.empty(B, dtype=torch.int64, device=dev)
@@ -114,7 +115,18 @@ def main():
             out, gathered = d.lookup_batch(q), None
         e1.record()
         torch.cuda.synchronize()
-        assert torch.equal(out[0::2], ids), "positive queries must return the sampled ids"
+        # positives return the sampled ids -- except where the (regular) index holds a k-mer AND its
+        # reverse complement as two entries (a 32-base reverse palindrome in the text: ~0.6 expected
+        # in 2.5e9 random bases); those few must then agree with the reference CPU dictionary
+        bad = (out[0::2] != ids).nonzero().flatten()
+        if bad.numel():
+            from oracle import ref
+            assert bad.numel() <= 16 and ref.available(31), "positive queries must return the sampled ids"
+            rd = ref.RefDictionary(idx, max_k=31)
+            want = rd.lookup(q[0::2][bad].cpu().numpy().view(np.uint64))
+            rd.close()
+            assert (out[0::2][bad].cpu().numpy().view(np.uint64) == want).all(), "ids differ from the reference CPU dictionary"
+            rc_twins += int(bad.numel())
         if b == 0:
             if rank == 0 and a.oracle_sample:
                 from oracle import ref
@@ -162,7 +174,7 @@ def main():
                                    "ids_bytes_to_rank0": (world - 1) * n_batches * B * 8},
             "per_batch_ms_rank0": per_batch_ms,
             "lookup_only": {"ms": lookup_only_ms, "lookups_per_s": nq / lookup_only_ms * 1e3},
-            "random_kmers_found": found_neg, "checked_vs_reference": oracle_checked,
+            "random_kmers_found": found_neg, "reverse_palindrome_twins_rank0": rc_twins, "checked_vs_reference": oracle_checked,
             "build_s": build_s, "open_s": open_s}), flush=True)
     d.close()
     if world > 1:

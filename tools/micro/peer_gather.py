@@ -36,7 +36,7 @@ def main():
     local_out = torch.empty(B, dtype=torch.int64, device=dev)
     res = {}
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for name in ("local", "peer"):
+    for name in ("local", "peer"):  # see sshash_b200.sharded for the copy-engine variant
         for it in range(6):
             if it == 2:
                 torch.cuda.synchronize(); dist.barrier(); ev[0].record()
