@@ -63,10 +63,16 @@ class ShardedLookup:
 
     @classmethod
     def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25, mode: str = "auto"):
-        """mode "auto": peer stores when the process group runs on NCCL (GPUs of one box), else p2p."""
+        """mode "auto": on NCCL (GPUs of one box) peer stores for 2 ranks, copy engines beyond (rank dst's
+        NVLink ingress is the limit there and scattered 8-byte stores use it badly: measured at N=8 on
+        a 2.5e9-k-mer index 18.8 ms per 8 x 1.25e8 lookups with "copy", 25.9 with "peer", 26.8 with
+        "p2p"; at N=2 on cfg2 4.9 / 5.6 / 7.1 ms for peer / copy / p2p); p2p on other backends."""
         import torch.distributed as dist
         if mode == "auto":
-            mode = "peer" if (dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1) else "p2p"
+            if dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1:
+                mode = "peer" if dist.get_world_size(group) <= 2 else "copy"
+            else:
+                mode = "p2p"
         return cls(lambda k: dictionary.lookup_batch(k), words=dictionary.words, group=group,
                    chunk_queries=chunk_queries, lookup_into=lambda k, out: dictionary.lookup_batch(k, out=out), mode=mode)
 
