@@ -270,6 +270,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the lookup path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU: run on the CPUs next to this GPU so that the pinned host buffers of the
+        # e2e leg are allocated on its NUMA node (at N=1 the process keeps all cores for the CPU baseline)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(local_rank)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)   # CUDA order may differ from NVML's
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+        except Exception:
+            pass
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
