@@ -353,7 +353,23 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&fresh), words * 8 + kPadBytes);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fingerprinted codewords)");
         CU(cudaMemset(fresh, 0, words * 8 + kPadBytes));
-        CU(launch_build_fingerprints(ix, d->ctx, fpb, fresh, nullptr));
+        // minimizer filter: 16 bits per minimizer rounded up to a power of two of 32-bit words, only
+        // while it stays a few MB (L2-resident next to the hot slab); SSHASH_GPU_FILTER=0 disables it
+        uint32_t* filter = nullptr;
+        uint32_t filter_shift = 0;
+        const char* fl_env = std::getenv("SSHASH_GPU_FILTER");
+        if (!(fl_env && fl_env[0] == '0') && ix.codewords.size <= (4ull << 20)) {
+            uint32_t log_words = 4;
+            while ((32ull << log_words) < 16 * ix.codewords.size) ++log_words;
+            CU(cudaMalloc(reinterpret_cast<void**>(&filter), (4ull << log_words) + kPadBytes));
+            d->allocs.push_back(filter);
+            up.bytes += (4ull << log_words) + kPadBytes;
+            CU(cudaMemset(filter, 0, (4ull << log_words) + kPadBytes));
+            filter_shift = 32 - log_words;
+        }
+        CU(launch_build_fingerprints(ix, d->ctx, fpb, fresh, filter, filter_shift, nullptr));
+        ix.minimizer_filter = filter;
+        ix.filter_shift = filter_shift;
         CU(cudaDeviceSynchronize());
         void* old = const_cast<uint64_t*>(ix.codewords.data);
         d->allocs.erase(std::find(d->allocs.begin(), d->allocs.end(), old));

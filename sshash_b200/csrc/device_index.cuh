@@ -100,6 +100,18 @@ struct DeviceIndex {
     uint32_t mini_left[16], mini_right[16];
     uint64_t kmer_mask_lo, kmer_mask_hi;   // low 2k bits set (second word: bits 64..2k-1)
     uint64_t mmer_mask;                    // low 2m bits set
+    // MINIMIZER FILTER (small indexes only, nullptr otherwise): a blocked Bloom filter over the
+    // minimizers of the index, 16 bits per minimizer, two bits per key inside one 32-bit word, built at
+    // open time next to the fingerprints.  The STREAMING window lookups probe it right after the
+    // minimizer: a pass whose minimizer is not in the index ends there, before CityHash + PTHash +
+    // the codeword read (+23 % windows/s on cfg3, where half of the reads are negative and whole
+    // tiles of windows fail together).  lookup_kernel does not use it: measured -3 % on positives
+    // (the probe) and +1 % on uniform random negatives -- ~15 % of random k-mers have a minimizer
+    // that IS in the index (both are biased to small hashes), so a warp almost never fails as a whole.
+    // Only kept when it is small enough to stay L2-resident with the rest.
+    const uint32_t* minimizer_filter;
+    uint32_t filter_shift;                 // word index = hash >> filter_shift
+    uint32_t pad2_;
 };
 
 #ifdef __CUDACC__
@@ -478,9 +490,22 @@ __device__ __forceinline__ Hash128 skew_hash(const DevPhf& f, Kmer<2> x) { retur
 // Fingerprint of a minimizer (cw_fp_bits <= 32 bits).  In a canonical index the text at a bucket
 // offset may hold the reverse complement of the minimizer (compute_minimizer_tuples.cpp:76-86), so
 // the fingerprint is taken of the smaller of the two forms there.
-__device__ __forceinline__ uint32_t minimizer_fingerprint(const DeviceIndex& ix, uint64_t minimizer) {
+// 32-bit key of a minimizer for the fingerprint and the filter: folded halves of its canonical form
+__device__ __forceinline__ uint32_t minimizer_key32(const DeviceIndex& ix, uint64_t minimizer) {
     if (ix.canonical) { uint64_t r = mmer_rc(minimizer, ix.m); minimizer = r < minimizer ? r : minimizer; }
-    return (((uint32_t)minimizer ^ (uint32_t)(minimizer >> 32)) * 0x9e3779b1u) >> (32 - ix.cw_fp_bits);
+    return (uint32_t)minimizer ^ (uint32_t)(minimizer >> 32);
+}
+__device__ __forceinline__ uint32_t fingerprint_of_key(const DeviceIndex& ix, uint32_t key32) {
+    return (key32 * 0x9e3779b1u) >> (32 - ix.cw_fp_bits);
+}
+__device__ __forceinline__ uint32_t minimizer_fingerprint(const DeviceIndex& ix, uint64_t minimizer) {
+    return fingerprint_of_key(ix, minimizer_key32(ix, minimizer));
+}
+// filter slot of a key: word index and the two bits inside the word
+__device__ __forceinline__ void filter_slot(uint32_t key32, uint32_t shift, uint32_t& word, uint32_t& mask) {
+    word = (key32 * 0x9e3779b1u) >> shift;
+    const uint32_t g = (key32 ^ (key32 >> 15)) * 0x85ebca6bu;
+    mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31u));
 }
 
 // sparse_and_skew_index::lookup (sparse_and_skew_index.hpp:112-137): minimizer -> bucket.
@@ -489,11 +514,19 @@ __device__ __forceinline__ uint32_t minimizer_fingerprint(const DeviceIndex& ix,
 // USE_FP: reject a minimizer whose slot belongs to a different minimizer (returns 0 = no bucket).
 // Only the ids-only paths may use it: a full lookup_result needs the bucket type of the (wrong)
 // slot to reproduce minimizer_found (spss.hpp:51-65).
-template <int W, bool USE_FP>
+template <int W, bool USE_FP, bool USE_FILTER = false>
 __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t minimizer, Kmer<W> skew_key,
                                               uint64_t& first, bool& heavy) {
     uint32_t fp = 0;
-    if (USE_FP) fp = minimizer_fingerprint(ix, minimizer);   // before the loads: only 32 bits stay live across them
+    if (USE_FP) {
+        const uint32_t key32 = minimizer_key32(ix, minimizer);
+        if (USE_FILTER && ix.minimizer_filter) {
+            uint32_t word, mask;
+            filter_slot(key32, ix.filter_shift, word, mask);
+            if ((ld32<true>(ix.minimizer_filter + word) & mask) != mask) return 0;   // not a minimizer of this index
+        }
+        fp = fingerprint_of_key(ix, key32);                   // before the loads: only 32 bits stay live across them
+    }
     uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
     // entries are exactly 32 bits wide whenever the reference's codeword has <= 24 bits (api.cu)
     uint64_t code = ix.codewords.width == 32 ? (uint64_t)ld32<false>(reinterpret_cast<const uint32_t*>(ix.codewords.data) + id)
@@ -531,11 +564,11 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
 // FULL = also produce minimizer_found exactly (needs the m-mer check of spss.hpp:46-65); without
 // it the k-mer comparison alone decides, which yields the same ids (a k-mer match implies the
 // m-mer match because the minimizer is a substring of the k-mer at pos_in_kmer).
-template <int W, bool FULL>
+template <int W, bool FULL, bool FILTER = false>
 __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<W> x, Minimizer mi, LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     uint64_t first; bool heavy;
-    uint32_t n = bucket_of<W, !FULL>(ix, mi.value, x, first, heavy);
+    uint32_t n = bucket_of<W, !FULL, FILTER>(ix, mi.value, x, first, heavy);
     if (!FULL && n == 0) { result_clear(res, false); return false; }
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {
@@ -579,13 +612,13 @@ __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x,
 
 // Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)
 // + spss::lookup_canonical (spss.hpp:75-112, _lookup_canonical :237-247, __lookup_canonical :249-275)
-template <int W, bool FULL>
+template <int W, bool FULL, bool FILTER = false>
 __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kmer<W> x, Kmer<W> xr, Minimizer mi,
                                                       LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     Kmer<W> canon = kmer_lt(x, xr) ? x : xr;            // std::min(uint_kmer, uint_kmer_rc), dictionary.cpp:53
     uint64_t first; bool heavy;
-    uint32_t n = bucket_of<W, !FULL>(ix, mi.value, canon, first, heavy);
+    uint32_t n = bucket_of<W, !FULL, FILTER>(ix, mi.value, canon, first, heavy);
     if (!FULL && n == 0) { result_clear(res, false); return false; }
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {

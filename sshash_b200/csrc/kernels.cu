@@ -18,7 +18,10 @@ namespace {
 constexpr int kBlock = 256;
 // 6 resident CTAs/SM (<= 40 registers, 75 % occupancy): measured best on B200 for both the L2-resident
 // and the HBM-resident case (sweep over 3/4/5/6/8 in profiles/r1_notes.md)
-constexpr int kLookupMinBlocks = 6;
+#ifndef SSHASH_LOOKUP_MINB
+#define SSHASH_LOOKUP_MINB 6
+#endif
+constexpr int kLookupMinBlocks = SSHASH_LOOKUP_MINB;
 // the canonical flow on 128-bit k-mers keeps x, its reverse complement and two candidate k-mers
 // live and spills ~100 bytes at 40 registers; measured on a 5e8-k-mer k=63 canonical index it is
 // still fastest with 6 resident CTAs (14.2 G lookups/s vs 13.4 with 5, 13.3 with 4)
@@ -170,7 +173,8 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
 // m-mer found there in `strings` and ORs  codeword | fp << w  into the zeroed output vector.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
-build_fingerprints_kernel(const __grid_constant__ DeviceIndex ix, uint32_t fp_bits, unsigned long long* __restrict__ out) {
+build_fingerprints_kernel(const __grid_constant__ DeviceIndex ix, uint32_t fp_bits, unsigned long long* __restrict__ out,
+                          uint32_t* __restrict__ filter, uint32_t filter_shift) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint32_t w = ix.codewords.width, wo = w + fp_bits;
     DeviceIndex fx = ix;                      // only canonical / m / cw_fp_bits are read by the fingerprint
@@ -184,7 +188,13 @@ build_fingerprints_kernel(const __grid_constant__ DeviceIndex ix, uint32_t fp_bi
             const uint32_t size = (uint32_t)(code & 63) + 2;
             off = compact_get<false>(ix.mid_load, ix.begin_buckets_of_size[size] + (code >> 6) * size);
         } else off = compact_get<false>(ix.heavy, code >> 5);           // (code >> 2) >> 3 = begin of the heavy bucket
-        const uint64_t v = entry | ((uint64_t)minimizer_fingerprint(fx, read_mmer(ix, off, ix.m)) << w);
+        const uint32_t key32 = minimizer_key32(fx, read_mmer(ix, off, ix.m));
+        if (filter) {                                    // the minimizer filter (device_index.cuh), same pass
+            uint32_t word, mask;
+            filter_slot(key32, filter_shift, word, mask);
+            atomicOr(filter + word, mask);
+        }
+        const uint64_t v = entry | ((uint64_t)fingerprint_of_key(fx, key32) << w);
         const uint64_t pos = id * wo, word = pos >> 6;
         const uint32_t s = (uint32_t)pos & 63u;
         atomicOr(out + word, (unsigned long long)(v << s));
@@ -578,14 +588,14 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                 LookupResult res;
                 if (canonical) {                                // dictionary.cpp:24-42
                     bool found;
-                    if (mf.value < mr.value) found = lookup_canonical_with<W, false>(ix, x, xr, mf, res);
-                    else if (mr.value < mf.value) found = lookup_canonical_with<W, false>(ix, x, xr, mr, res);
+                    if (mf.value < mr.value) found = lookup_canonical_with<W, false, true>(ix, x, xr, mf, res);
+                    else if (mr.value < mf.value) found = lookup_canonical_with<W, false, true>(ix, x, xr, mr, res);
                     else {
-                        found = lookup_canonical_with<W, false>(ix, x, xr, mf, res);
-                        if (!found) found = lookup_canonical_with<W, false>(ix, x, xr, mr, res);
+                        found = lookup_canonical_with<W, false, true>(ix, x, xr, mf, res);
+                        if (!found) found = lookup_canonical_with<W, false, true>(ix, x, xr, mr, res);
                     }
                     store_window(win_id, win_aux, w0 + w, res, found && res.kmer_orientation < 0, w == 0, k);
-                } else if (lookup_regular_with<W, false>(ix, x, mf, res)) {
+                } else if (lookup_regular_with<W, false, true>(ix, x, mf, res)) {
                     store_window(win_id, win_aux, w0 + w, res, false, w == 0, k);
                 } else {
                     park = true;
@@ -600,7 +610,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                 queued -= 32;
                 const uint32_t e = queued + lane;
                 LookupResult res;
-                const bool found = lookup_regular_with<W, false>(ix, q.get(e), Minimizer{q.mini[e], q.pos[e]}, res);
+                const bool found = lookup_regular_with<W, false, true>(ix, q.get(e), Minimizer{q.mini[e], q.pos[e]}, res);
                 store_window(win_id, win_aux, q.widx[e] & ~kAuxFirstOfRead, res, found, (q.widx[e] & kAuxFirstOfRead) != 0, k);
                 __syncwarp();
             }
@@ -609,7 +619,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
     }
     if (!canonical && lane < queued) {
         LookupResult res;
-        const bool found = lookup_regular_with<W, false>(ix, q.get(lane), Minimizer{q.mini[lane], q.pos[lane]}, res);
+        const bool found = lookup_regular_with<W, false, true>(ix, q.get(lane), Minimizer{q.mini[lane], q.pos[lane]}, res);
         store_window(win_id, win_aux, q.widx[lane] & ~kAuxFirstOfRead, res, found, (q.widx[lane] & kAuxFirstOfRead) != 0, k);
     }
 }
@@ -1040,10 +1050,10 @@ cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const
 }
 
 cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
-                                      cudaStream_t stream) {
+                                      uint32_t* filter, uint32_t filter_shift, cudaStream_t stream) {
     if (ix.codewords.size == 0) return cudaSuccess;
     return launch(build_fingerprints_kernel, grid_for(ix.codewords.size, ctx.sm_count, 8), stream, ctx, ix, fp_bits,
-                  reinterpret_cast<unsigned long long*>(out));
+                  reinterpret_cast<unsigned long long*>(out), filter, filter_shift);
 }
 
 uint64_t streaming_anchor_bytes(uint64_t num_reads) { return num_reads * kAnchorsPerRead * sizeof(Anchor); }

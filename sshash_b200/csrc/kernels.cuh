@@ -44,9 +44,10 @@ cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
                           cudaStream_t stream);
 
 // open time: re-encode ix.codewords (verbatim) into `out` (zeroed, width + fp_bits per entry) with
-// a fingerprint of each slot's minimizer above the codeword
+// a fingerprint of each slot's minimizer above the codeword; `filter` (nullable, zeroed, 2^(32 - filter_shift)
+// words) receives the blocked Bloom filter over the same minimizers
 cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
-                                      cudaStream_t stream);
+                                      uint32_t* filter, uint32_t filter_shift, cudaStream_t stream);
 
 // Reads are spans of `bases`: read r = [read_begins[r], read_ends[r]) (contiguous reads:
 // read_offsets and read_offsets + 1).
