@@ -556,6 +556,7 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
             } else if (w < nwin && !valid) { win_id[w0 + w] = ~0ull; win_aux[w0 + w] = w == 0 ? kAuxFirstOfRead : 0; }
             // ---- m-mer hashes of the tile, both strands (mixer_64::hash, hash_util.hpp:91) -------------
             __syncwarp();
+#ifdef SSHASH_STREAM_EXACT_MIN
 #pragma unroll
             for (int blk = 0; blk < NBLK; ++blk) {
                 const uint32_t p = 32 * blk + lane;
@@ -582,6 +583,48 @@ stream_windows_kernel(const __grid_constant__ DeviceIndex ix, const char* __rest
                 else { mr.pos = n - 1 - pr; mr.value = kmer_bits_at(xr, mr.pos, m); }
                 if (bf == ~0ull) mf.pos = 0;
             }
+#else
+            // Per tile position p the two strands' hashes are reduced to their 25 high bits and packed with
+            // the position both ways: lo = h25 << 7 | p, hi = h25 << 7 | (127 - p).  A window's minimum over
+            // the lo keys names the LEFTMOST position of its smallest h25, over the hi keys the RIGHTMOST;
+            // when they agree exactly one m-mer has the smallest 25 bits, hence the smallest 64-bit hash,
+            // whichever tie rule applies (leftmost on the k-mer, include/util.hpp:262-283; rightmost =
+            // leftmost on the reverse complement).  Otherwise -- a repeated m-mer, a 2^-25 collision, or
+            // h25 all ones (the reference's "no hash below UINT64_MAX" case) -- the exact scan decides.
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+                const uint32_t p = 32 * blk + lane;
+                if (p < 32 + n - 1) {
+                    const uint64_t mm = funnel64(word[blk], word[blk + 1], lane) & mmask;
+                    const uint32_t f25 = (uint32_t)((((mm * SSHASH_MIX_C) ^ magic) >> 39) << 7);
+                    const uint32_t r25 = (uint32_t)((((mmer_rc(mm, m) * SSHASH_MIX_C) ^ magic) >> 39) << 7);
+                    hf[p] = ((uint64_t)(f25 | (127u - p)) << 32) | (f25 | p);
+                    hr[p] = ((uint64_t)(r25 | (127u - p)) << 32) | (r25 | p);
+                }
+            }
+            __syncwarp();
+            Minimizer mf{~0ull, 0}, mr{~0ull, 0};
+            if (valid) {
+                uint32_t fl = ~0u, fr = ~0u, rl = ~0u, rr = ~0u;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint64_t a = hf[lane + i], c = hr[lane + i];
+                    fl = min(fl, (uint32_t)a); fr = min(fr, (uint32_t)(a >> 32));
+                    rl = min(rl, (uint32_t)c); rr = min(rr, (uint32_t)(c >> 32));
+                }
+                if (!have_xr) xr = kmer_rc(x, k);
+                const uint32_t pf = (fl & 127u) - lane, pr = (rl & 127u) - lane;     // positions inside the window
+                if (pf == 127u - (fr & 127u) - lane && (fl >> 7) != 0x1ffffffu) {
+                    mf.pos = pf; mf.value = kmer_bits_at(x, pf, m);
+                } else {
+                    mf = ix.m <= 16 ? compute_minimizer_exact<true>(x, k, m, magic) : compute_minimizer_exact<false>(x, k, m, magic);
+                }
+                if (pr == 127u - (rr & 127u) - lane && (rl >> 7) != 0x1ffffffu) {
+                    mr.pos = n - 1 - pr; mr.value = kmer_bits_at(xr, mr.pos, m);
+                } else {
+                    mr = ix.m <= 16 ? compute_minimizer_exact<true>(xr, k, m, magic) : compute_minimizer_exact<false>(xr, k, m, magic);
+                }
+            }
+#endif
             // ---- lookups ----------------------------------------------------------------------------
             bool park = false;
             if (valid) {

@@ -311,6 +311,44 @@ def test_low_complexity_queries_vs_oracle(dicts, name):
     o.close()
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_streaming_low_complexity_reads_vs_oracle(dicts, name):
+    """Streaming over reads made of homopolymers, short tandem repeats, indexed text with repeats
+    spliced in, and their mixtures: within a window several m-mers share one hash, so the window
+    minimizer of both strands is decided by the tie rules (leftmost on the k-mer, leftmost on its
+    reverse complement) -- the streaming kernel's packed 25-bit scan must hand those windows to
+    the exact scan.  Ids and all six counters against the C oracle."""
+    from oracle import port
+    g, d = golden(name), dicts(name)
+    o = port.OracleDictionary(g.index, g.max_k)
+    k = d.k()
+    rng = np.random.default_rng(11)
+    raw = g.z["read_bases"].tobytes().decode()
+    off = g.z["read_offsets"].astype(np.int64)
+    real = [raw[off[i]:off[i + 1]] for i in range(min(len(off) - 1, 60))]
+    reads = []
+    for period in range(1, 7):
+        for _ in range(12):
+            unit = "".join("ACGT"[c] for c in rng.integers(0, 4, period))
+            reads.append((unit * (300 // period + 1))[: int(rng.integers(k, 300))])
+    for r in real:
+        if len(r) < 2 * k:
+            continue
+        cut = int(rng.integers(k // 2, len(r) - k // 2))
+        unit = "".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(1, 4))))
+        reads.append(r[:cut] + unit * int(rng.integers(5, 40)) + r[cut:])      # a repeat inside indexed text
+        reads.append(r[:cut] + "N" + unit * 20)
+    reads += ["A" * (k - 1), "C" * k, "", "ACGT" * 100]
+    bases = "".join(reads).encode()
+    offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(r) for r in reads])
+    want_ids, _, want_rep = o.streaming_reads(bases, offsets)
+    got_ids, got_rep = d.streaming_batch(np.frombuffer(bases, dtype=np.uint8), offsets)
+    assert (got_ids == want_ids).all()
+    assert got_rep == want_rep
+    assert got_rep["num_kmers"] > 5000
+
+
 @pytest.mark.parametrize("name", WEIGHTED)
 def test_weights(dicts, name):
     """dictionary::weight (src/dictionary.cpp:96-100) vs the reference's goldens and, for every
