@@ -60,8 +60,6 @@ struct Workspace {
     static constexpr int kSlots = 3;
     Slot slots[kSlots];
     // streaming scratch
-    void* d_bases = nullptr; uint64_t bases_cap = 0;
-    uint64_t* d_read_offsets = nullptr; uint64_t ro_cap = 0;
     uint64_t* d_win_offsets = nullptr; uint64_t wo_cap = 0;
     uint64_t* d_block_sums = nullptr; uint64_t bs_cap = 0;
     uint64_t* d_win_id = nullptr; uint64_t* d_win_aux = nullptr; uint64_t win_cap = 0;
@@ -69,6 +67,15 @@ struct Workspace {
     void* d_anchors = nullptr; uint64_t anchors_cap = 0;
     unsigned long long* d_counters = nullptr;
     unsigned long long* h_counters = nullptr;   // pinned
+    // host-buffer streaming pipeline: two staging sets so that the H2D copy of chunk c+1 overlaps the
+    // kernels of chunk c (the window scratch above is shared: kernels stay on one stream)
+    struct StreamSlot {
+        void* d_bases = nullptr; uint64_t bases_cap = 0;
+        uint64_t* d_ro = nullptr; uint64_t ro_cap = 0;
+        uint64_t* d_ids = nullptr; uint64_t ids_cap = 0;
+        cudaEvent_t ready = nullptr, free = nullptr;
+    } sslots[2];
+    cudaStream_t copy_stream = nullptr;
     // file driver with device-side record parsing
     uint8_t* d_raw = nullptr; uint64_t raw_cap = 0;
     uint64_t* d_tiles = nullptr; uint64_t tiles_cap = 0;
@@ -83,10 +90,16 @@ struct Workspace {
             if (s.d_tmp) cudaFree(s.d_tmp);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
-        cudaFree(d_bases); cudaFree(d_read_offsets); cudaFree(d_win_offsets); cudaFree(d_block_sums);
+        cudaFree(d_win_offsets); cudaFree(d_block_sums);
         cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters); cudaFree(d_anchors);
         if (h_counters) cudaFreeHost(h_counters);
         cudaFree(d_raw); cudaFree(d_tiles); cudaFree(d_line_start); cudaFree(d_spans);
+        for (auto& ss : sslots) {
+            cudaFree(ss.d_bases); cudaFree(ss.d_ro); cudaFree(ss.d_ids);
+            if (ss.ready) cudaEventDestroy(ss.ready);
+            if (ss.free) cudaEventDestroy(ss.free);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto* h : h_file) if (h) cudaFreeHost(h);
     }
 };
@@ -100,6 +113,13 @@ cudaError_t ensure(T*& p, uint64_t& cap, uint64_t need_bytes) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), bytes);
     if (e == cudaSuccess) cap = bytes;
     return e;
+}
+
+uint64_t env_bytes(const char* name, uint64_t dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    const unsigned long long v = std::strtoull(e, nullptr, 10);
+    return v ? v : dflt;
 }
 
 bool is_device_pointer(const void* p) {
@@ -725,28 +745,38 @@ int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, c
         st = streaming_device(dict, w, bases, read_offsets, read_offsets + 1, num_reads, last - first + 1, kmer_ids, s);
         if (st) return st;
     } else {
-        // chunks of reads: <= 64 MB of bases each, staged through the workspace buffers
-        const uint64_t max_bases = 64ull << 20;
+        // Chunks of reads (<= 16 MB of bases, <= 1 Mi reads each) cycle through two staging sets: the
+        // H2D copy of chunk c+1 runs on a copy stream while the kernels of chunk c run on the compute
+        // stream.  Offsets are copied as they are (absolute); the kernels get the staging pointer
+        // rebased by the chunk's first offset instead of a rewritten offsets array.
+        // SSHASH_GPU_STREAM_CHUNK: bases per chunk (tests use tiny chunks to exercise the pipeline)
+        const uint64_t max_bases = env_bytes("SSHASH_GPU_STREAM_CHUNK", 16ull << 20), max_reads = 1ull << 20;
+        if (!w.copy_stream) CU(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+        for (auto& ss : w.sslots) {
+            if (!ss.ready) CU(cudaEventCreateWithFlags(&ss.ready, cudaEventDisableTiming));
+            if (!ss.free) CU(cudaEventCreateWithFlags(&ss.free, cudaEventDisableTiming));
+        }
         uint64_t r0 = 0, win_done = 0;
-        std::vector<uint64_t> rel;
-        while (r0 < num_reads) {
+        for (int c = 0; r0 < num_reads; ++c) {
             uint64_t r1 = r0 + 1;
-            while (r1 < num_reads && read_offsets[r1 + 1] - read_offsets[r0] <= max_bases) ++r1;
-            const uint64_t nb = read_offsets[r1] - read_offsets[r0], nr = r1 - r0;
-            rel.resize(nr + 1);
+            while (r1 < num_reads && r1 - r0 < max_reads && read_offsets[r1 + 1] - read_offsets[r0] <= max_bases) ++r1;
+            const uint64_t first = read_offsets[r0], nb = read_offsets[r1] - first, nr = r1 - r0;
             uint64_t nwin = 0;
-            for (uint64_t i = 0; i <= nr; ++i) rel[i] = read_offsets[r0 + i] - read_offsets[r0];
-            for (uint64_t i = 0; i < nr; ++i) { uint64_t len = rel[i + 1] - rel[i]; if (len >= k) nwin += len - k + 1; }
-            CU(ensure(w.d_bases, w.bases_cap, nb + kPadBytes));
-            CU(ensure(w.d_read_offsets, w.ro_cap, (nr + 1) * 8));
-            if (kmer_ids) CU(ensure(w.d_ids, w.ids_cap, (nwin + 1) * 8));
-            CU(cudaMemcpyAsync(w.d_bases, bases + read_offsets[r0], nb, cudaMemcpyHostToDevice, s));
-            CU(cudaMemcpyAsync(w.d_read_offsets, rel.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, s));
-            st = streaming_device(dict, w, static_cast<const char*>(w.d_bases), w.d_read_offsets, w.d_read_offsets + 1, nr, nwin + 1,
-                                  kmer_ids ? w.d_ids : nullptr, s);
+            for (uint64_t i = r0; i < r1; ++i) { const uint64_t len = read_offsets[i + 1] - read_offsets[i]; if (len >= k) nwin += len - k + 1; }
+            Workspace::StreamSlot& ss = w.sslots[c & 1];
+            if (c >= 2) CU(cudaEventSynchronize(ss.free));   // chunk c-2 is done with this staging set (ensure() may reallocate it)
+            CU(ensure(ss.d_bases, ss.bases_cap, nb + kPadBytes));
+            CU(ensure(ss.d_ro, ss.ro_cap, (nr + 1) * 8));
+            if (kmer_ids) CU(ensure(ss.d_ids, ss.ids_cap, (nwin + 1) * 8));
+            CU(cudaMemcpyAsync(ss.d_bases, bases + first, nb, cudaMemcpyHostToDevice, w.copy_stream));
+            CU(cudaMemcpyAsync(ss.d_ro, read_offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, w.copy_stream));
+            CU(cudaEventRecord(ss.ready, w.copy_stream));
+            CU(cudaStreamWaitEvent(s, ss.ready, 0));
+            const char* rebased = static_cast<const char*>(ss.d_bases) - first;
+            st = streaming_device(dict, w, rebased, ss.d_ro, ss.d_ro + 1, nr, nwin + 1, kmer_ids ? ss.d_ids : nullptr, s);
             if (st) return st;
-            if (kmer_ids && nwin) CU(cudaMemcpyAsync(kmer_ids + win_done, w.d_ids, nwin * 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));   // `rel` and the staging buffers are reused by the next chunk
+            if (kmer_ids && nwin) CU(cudaMemcpyAsync(kmer_ids + win_done, ss.d_ids, nwin * 8, cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(ss.free, s));
             win_done += nwin;
             r0 = r1;
         }
@@ -835,13 +865,6 @@ private:
     gzFile gz_ = nullptr;
     uint64_t pos_ = 0;
 };
-
-uint64_t env_bytes(const char* name, uint64_t dflt) {
-    const char* e = std::getenv(name);
-    if (!e || !*e) return dflt;
-    const unsigned long long v = std::strtoull(e, nullptr, 10);
-    return v ? v : dflt;
-}
 
 // *need_host_parser = true (and OK returned) when a single record does not fit a chunk: the caller
 // then runs the host line parser over the whole file instead.

@@ -123,6 +123,12 @@ def test_streaming_ids_and_report(dicts, name):
     assert [rep[k] for k in REPORT_KEYS] == g.z["stream_report"].tolist()
     _, rep2 = d.streaming_batch(g.z["read_bases"], g.z["read_offsets"], want_ids=False)
     assert rep2 == rep
+    # host buffers go through a double-buffered chunk pipeline: tiny chunks -> many chunks, same answer
+    for chunk in (200, 4096):
+        old = _set_env(SSHASH_GPU_STREAM_CHUNK=chunk)
+        ids3, rep3 = d.streaming_batch(g.z["read_bases"], g.z["read_offsets"])
+        _set_env(**old)
+        assert (ids3 == g.z["stream_ids"]).all() and rep3 == rep, chunk
 
 
 @pytest.mark.parametrize("name", ["se_k31_m13", "se_k63_m8_canon"])
