@@ -463,7 +463,8 @@ int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void
         return SSHASH_GPU_OK;
     }
     WorkspaceLease ws(d);
-    const uint64_t chunk = std::max<uint64_t>(1, (32ull << 20) / std::max(in_elem, out_elem));
+    // SSHASH_GPU_BATCH_CHUNK: bytes per pipeline chunk of the larger of the two element streams
+    const uint64_t chunk = std::max<uint64_t>(1, env_bytes("SSHASH_GPU_BATCH_CHUNK", 32ull << 20) / std::max(in_elem, out_elem));
     int c = 0;
     for (uint64_t off = 0; off < n; off += chunk, ++c) {
         const uint64_t cn = std::min(chunk, n - off);
