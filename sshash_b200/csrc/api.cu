@@ -401,6 +401,28 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         ix.codewords.mask = (w + fpb) >= 64 ? ~0ull : ((1ull << (w + fpb)) - 1);
         ix.cw_fp_bits = fpb;
     }
+    // WIDE ENTRIES (DeviceIndex::wide): opt-in with SSHASH_GPU_WIDE=1.  Measured on the 5e8-k-mer index
+    // (same box): forward-only positives 22.8 -> 26.5 G lookups/s, 50 % RC mix 17.6 -> 18.4, uniform
+    // random negatives 20.1 -> 17.3 (the 1 GB entry table loses the partial L2 residency the 290 MB
+    // codeword vector has), at 3x the device bytes: a win for positive-heavy batches only.
+    {
+        const char* we = std::getenv("SSHASH_GPU_WIDE");
+        const bool want = we && we[0] == '1';
+        const uint64_t text_bits = 2ull * (2ull * f.k - f.m);
+        if (want && up.error.empty() && ix.kmer_words == 1 && ix.codewords.size && f.k >= f.m && ix.cw_code_bits >= 1 &&
+            ix.cw_code_bits + text_bits <= 128) {
+            void* wide = nullptr;
+            const uint64_t bytes = ix.codewords.size * 16 + kPadBytes;
+            cudaError_t e = cudaMalloc(&wide, bytes);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(wide entries)");
+            d->allocs.push_back(wide);
+            up.bytes += bytes;
+            CU(cudaMemset(static_cast<uint8_t*>(wide) + ix.codewords.size * 16, 0, kPadBytes));
+            CU(launch_build_wide(ix, d->ctx, wide, nullptr));
+            CU(cudaDeviceSynchronize());
+            ix.wide = static_cast<const ulonglong2*>(wide);
+        }
+    }
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
     d->info.device_bytes = up.bytes;
     return SSHASH_GPU_OK;

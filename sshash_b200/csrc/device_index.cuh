@@ -112,6 +112,14 @@ struct DeviceIndex {
     const uint32_t* minimizer_filter;
     uint32_t filter_shift;                 // word index = hash >> filter_shift
     uint32_t pad2_;
+    // WIDE ENTRIES (opt-in, SSHASH_GPU_WIDE=1; k <= 31 in the 64-bit build; nullptr otherwise): one
+    // 16-byte record per MPHF slot = codeword | TEXT << cw_code_bits, where TEXT is the 2(2k - m) bits
+    // of `strings` around the slot's bucket offset, [offset - (k - m), offset + k): every k-mer that
+    // has this minimizer at any position lies inside it.  For a SINGLETON bucket (94-97 % of the
+    // minimizers) the ids-only lookup compares against this copy instead of reading `strings`: one
+    // cold fetch per pass instead of two (codeword + strings).  Built on the GPU at open time from
+    // the arrays above; other bucket types fall back to the regular route.
+    const ulonglong2* wide;
 };
 
 #ifdef __CUDACC__
@@ -162,6 +170,12 @@ __device__ __forceinline__ uint32_t ld32(const uint32_t* __restrict__ p) {
     uint32_t v;
     if (HOT) asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<true>()));
     else asm("ld.global.nc.L2::cache_hint.L2::64B.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<false>()));
+    return v;
+}
+
+__device__ __forceinline__ ulonglong2 ld128_cold(const ulonglong2* __restrict__ p) {
+    ulonglong2 v;
+    asm("ld.global.nc.L2::cache_hint.L2::64B.v2.b64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_policy<false>()));
     return v;
 }
 
@@ -675,6 +689,79 @@ __device__ __forceinline__ bool lookup_canonical(const DeviceIndex& ix, Kmer<W> 
 #pragma unroll 1
     for (int t = 0;; ++t) {                             // one inlined copy of the pass
         if (lookup_canonical_with<W, FULL>(ix, x, xr, mi, res)) return true;
+        if (!tie || t == 1) return false;
+        mi = mr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WIDE-ENTRY passes (ids-only, 64-bit k-mers).  Same decisions as lookup_regular_with /
+// lookup_canonical_with; for a SINGLETON bucket the candidate k-mers come out of the entry's copy of
+// the text instead of `strings`.  ko = offset - pos sits at bit 2 * ((k - m) - pos) of TEXT.
+// ------------------------------------------------------------------------------------------------
+struct WideEntry { uint64_t code, text_lo, text_hi; };
+__device__ __forceinline__ WideEntry load_wide(const DeviceIndex& ix, uint64_t minimizer) {
+    const uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));
+    const ulonglong2 e = ld128_cold(ix.wide + id);
+    const uint32_t w = ix.cw_code_bits;                  // in [1, 63]
+    return {e.x & low_mask(w), (e.x >> w) | (e.y << (64 - w)), e.y >> w};
+}
+__device__ __forceinline__ uint64_t wide_kmer(const DeviceIndex& ix, const WideEntry& e, uint32_t pos) {
+    const uint32_t s = 2 * (ix.k - ix.m - pos);          // <= 2 (k - m) <= 60
+    return (s == 0 ? e.text_lo : (e.text_lo >> s) | (e.text_hi << (64 - s))) & ix.kmer_mask_lo;
+}
+__device__ __forceinline__ bool wide_finish(const DeviceIndex& ix, uint64_t ko, int64_t orientation, LookupResult& res) {
+    const uint32_t k = ix.k;
+    uint64_t sb, se;
+    const uint64_t sid = locate_string(ix, ko, sb, se);
+    if (!(ko < se - k + 1)) return false;                // spss.hpp:233 / :266
+    res.kmer_id = ko - sid * (k - 1);
+    res.kmer_id_in_string = ko - sb;
+    res.kmer_offset = ko;
+    res.kmer_orientation = orientation;
+    res.string_id = sid; res.string_begin = sb; res.string_end = se;
+    res.minimizer_found = 1;
+    return true;
+}
+
+__device__ __forceinline__ bool lookup_regular_wide(const DeviceIndex& ix, Kmer<1> x, LookupResult& res) {
+    const Minimizer mi = compute_minimizer(ix, x);
+    const WideEntry e = load_wide(ix, mi.value);
+    if (e.code & 1) return lookup_regular_with<1, false>(ix, x, mi, res);     // MIDLOAD / HEAVYLOAD: the regular route
+    const uint64_t off = e.code >> 1;
+    if (off >= mi.pos && wide_kmer(ix, e, mi.pos) == x.lo && wide_finish(ix, off - mi.pos, 1, res)) return true;
+    result_clear(res, true);
+    return false;
+}
+
+__device__ __forceinline__ bool lookup_canonical_wide_with(const DeviceIndex& ix, Kmer<1> x, Kmer<1> xr, Minimizer mi,
+                                                           LookupResult& res) {
+    const WideEntry e = load_wide(ix, mi.value);
+    if (e.code & 1) return lookup_canonical_with<1, false>(ix, x, xr, mi, res);
+    const uint64_t off = e.code >> 1;
+    const uint32_t pa = mi.pos, pb = ix.k - ix.m - mi.pos;                      // spss.hpp:243-246: pa first, then pb
+    if (off >= pa) {
+        const uint64_t r = wide_kmer(ix, e, pa);
+        if ((r == x.lo || r == xr.lo) && wide_finish(ix, off - pa, r == xr.lo ? -1 : 1, res)) return true;
+    }
+    if (off >= pb) {
+        const uint64_t r = wide_kmer(ix, e, pb);
+        if ((r == x.lo || r == xr.lo) && wide_finish(ix, off - pb, r == xr.lo ? -1 : 1, res)) return true;
+    }
+    result_clear(res, true);
+    return false;
+}
+
+// dictionary::lookup_canonical(Kmer), src/dictionary.cpp:24-42, over wide entries
+__device__ __forceinline__ bool lookup_canonical_wide(const DeviceIndex& ix, Kmer<1> x, LookupResult& res) {
+    const Kmer<1> xr = kmer_rc(x, ix.k);
+    const Minimizer mf = compute_minimizer(ix, x);
+    const Minimizer mr = compute_minimizer(ix, xr);
+    const bool tie = mf.value == mr.value;
+    Minimizer mi = mr.value < mf.value ? mr : mf;
+#pragma unroll 1
+    for (int t = 0;; ++t) {
+        if (lookup_canonical_wide_with(ix, x, xr, mi, res)) return true;
         if (!tie || t == 1) return false;
         mi = mr;
     }

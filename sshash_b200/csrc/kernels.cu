@@ -111,7 +111,7 @@ template <> struct RcQueue<2> {
 // 32 are parked (or the input is exhausted), 32 parked reverse complements.  CANON selects the
 // canonical (src/dictionary.cpp:24-56) or the regular (:7-22, :64-78) flow at compile time so that
 // each instantiation carries only its own path.
-template <int W, int MODE, bool ASCII, bool CANON, int MINB>
+template <int W, int MODE, bool ASCII, bool CANON, int MINB, bool WIDE = false>
 __global__ void __launch_bounds__(kBlock, MINB)
 lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ queries, uint64_t n, int check_rc,
               uint64_t* __restrict__ ids, sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
@@ -149,8 +149,13 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
         bool found = false;
         LookupResult r;
         if (active) {
-            if (CANON) found = lookup_canonical<W, FULL>(ix, x, r);
-            else found = lookup_regular<W, FULL>(ix, x, r);
+            if constexpr (WIDE) {                              // wide entries: ids-only, 64-bit k-mers (device_index.cuh)
+                if (CANON) found = lookup_canonical_wide(ix, x, r);
+                else found = lookup_regular_wide(ix, x, r);
+            } else {
+                if (CANON) found = lookup_canonical<W, FULL>(ix, x, r);
+                else found = lookup_regular<W, FULL>(ix, x, r);
+            }
         }
         const bool park = active && fresh && two_pass && !found;
         if (active && !park) {
@@ -199,6 +204,36 @@ build_fingerprints_kernel(const __grid_constant__ DeviceIndex ix, uint32_t fp_bi
         const uint32_t s = (uint32_t)pos & 63u;
         atomicOr(out + word, (unsigned long long)(v << s));
         if (s + wo > 64) atomicOr(out + word + 1, (unsigned long long)(v >> (64 - s)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// open-time construction of the WIDE ENTRIES (device_index.cuh): one thread per MPHF slot copies the
+// slot's codeword and, for a SINGLETON bucket, the 2(2k - m) bits of `strings` around its offset
+// ([offset - (k - m), offset + k); positions before the start of the text read as zero).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+build_wide_kernel(const __grid_constant__ DeviceIndex ix, ulonglong2* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t w = ix.cw_code_bits, span = ix.k - ix.m, text_bits = 2 * (2 * ix.k - ix.m);
+    for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < ix.codewords.size; id += stride) {
+        const uint64_t code = compact_get<false>(ix.codewords, id) & low_mask(w);
+        uint64_t lo = 0, hi = 0;
+        if ((code & 1) == 0) {
+            const uint64_t off = code >> 1;
+            if (off >= span) {
+                lo = read_word64(ix.strings, 2 * (off - span));
+                hi = read_word64(ix.strings, 2 * (off - span) + 64);
+            } else {
+                const uint32_t sh = 2 * (uint32_t)(span - off);          // in [2, 60]
+                const uint64_t a = read_word64(ix.strings, 0), b = read_word64(ix.strings, 64);
+                lo = a << sh;
+                hi = (b << sh) | (a >> (64 - sh));
+            }
+            if (text_bits <= 64) { lo &= low_mask(text_bits); hi = 0; }
+            else hi &= low_mask(text_bits - 64);
+        }
+        out[id] = make_ulonglong2(code | (lo << w), (lo >> (64 - w)) | (hi << w));   // w in [1, 63], w + text_bits <= 128
     }
 }
 
@@ -1046,6 +1081,15 @@ cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const voi
 #define SSHASH_LAUNCH(W, MODE, ASCII) \
     err = ix.canonical ? launch(lookup_kernel<W, MODE, ASCII, true, (W == 2 ? kLookupMinBlocksWideCanon : kLookupMinBlocks)>, grid, stream, ctx, ix, queries, n, crc, ids, full, member) \
                        : launch(lookup_kernel<W, MODE, ASCII, false, kLookupMinBlocks>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
+#define SSHASH_LAUNCH_WIDE(MODE, ASCII) \
+    err = ix.canonical ? launch(lookup_kernel<1, MODE, ASCII, true, kLookupMinBlocks, true>, grid, stream, ctx, ix, queries, n, crc, ids, full, member) \
+                       : launch(lookup_kernel<1, MODE, ASCII, false, kLookupMinBlocks, true>, grid, stream, ctx, ix, queries, n, crc, ids, full, member)
+    if (ix.wide && ix.kmer_words == 1 && mode != 1) {      // ids / membership over wide entries
+        if (mode == 0) { if (ascii) SSHASH_LAUNCH_WIDE(0, true); else SSHASH_LAUNCH_WIDE(0, false); }
+        else { if (ascii) SSHASH_LAUNCH_WIDE(2, true); else SSHASH_LAUNCH_WIDE(2, false); }
+        return err;
+    }
+#undef SSHASH_LAUNCH_WIDE
 #define SSHASH_DISPATCH_MODE(W, ASCII)                     \
     do {                                                   \
         if (mode == 0) SSHASH_LAUNCH(W, 0, ASCII);         \
@@ -1097,6 +1141,11 @@ cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ct
     if (ix.codewords.size == 0) return cudaSuccess;
     return launch(build_fingerprints_kernel, grid_for(ix.codewords.size, ctx.sm_count, 8), stream, ctx, ix, fp_bits,
                   reinterpret_cast<unsigned long long*>(out), filter, filter_shift);
+}
+
+cudaError_t launch_build_wide(const DeviceIndex& ix, const LaunchCtx& ctx, void* out, cudaStream_t stream) {
+    if (ix.codewords.size == 0) return cudaSuccess;
+    return launch(build_wide_kernel, grid_for(ix.codewords.size, ctx.sm_count, 8), stream, ctx, ix, static_cast<ulonglong2*>(out));
 }
 
 uint64_t streaming_anchor_bytes(uint64_t num_reads) { return num_reads * kAnchorsPerRead * sizeof(Anchor); }

@@ -49,6 +49,10 @@ cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
 cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,
                                       uint32_t* filter, uint32_t filter_shift, cudaStream_t stream);
 
+// open time: the 16-byte wide entries (codeword + the text around a singleton bucket's offset), one per
+// MPHF slot, into `out` (ix.codewords.size entries); see DeviceIndex::wide
+cudaError_t launch_build_wide(const DeviceIndex& ix, const LaunchCtx& ctx, void* out, cudaStream_t stream);
+
 // Reads are spans of `bases`: read r = [read_begins[r], read_ends[r]) (contiguous reads:
 // read_offsets and read_offsets + 1).
 // win_offsets[r] = number of windows in reads [0, r), computed on the device from the spans

@@ -474,3 +474,47 @@ def test_sharded_lookup_with_peer_store_gather_two_gpus():
     line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
     r = json.loads(line)
     assert r["world"] == 2 and r["peer_ms"] > 0
+
+
+@pytest.mark.parametrize("name", ["se_k31_m13", "sakai_k31_m13_weighted", "ecoli_k31_m11_canon_weighted", "sal100_k31_m11_canon"])
+def test_wide_entries_layout_gives_the_same_answers(dicts, name):
+    """Indexes that do not fit L2 get 16-byte wide entries (codeword + the text around a singleton
+    bucket's offset) and the ids-only lookups compare against that copy instead of reading
+    `strings`.  Forced here on small fixtures (SSHASH_GPU_WIDE=1): ids, membership, no-RC lookups,
+    ASCII input, negatives and low-complexity k-mers must equal the goldens / the C oracle."""
+    import sshash_b200
+    from oracle import port
+    g, d = golden(name), dicts(name)
+    old = _set_env(SSHASH_GPU_WIDE=1)
+    dw = sshash_b200.Dictionary(g.index, device=0, max_k=g.max_k)
+    _set_env(**old)
+    try:
+        if dw.info["device_bytes"] < d.info["device_bytes"] + 16 * d.info["num_minimizers"]:
+            pytest.skip("codeword + text do not fit 128 bits for this k, m")
+        q = g.z["queries"]
+        assert (dw.lookup_batch(q) == g.z["ids"]).all()
+        assert (dw.is_member_batch(q) == (g.z["ids"] != INVALID)).all()
+        assert (dw.lookup_batch(q, check_reverse_complement=False) == d.lookup_batch(q, check_reverse_complement=False)).all()
+        full = dw.lookup_batch(q, full=True)                      # full records keep the regular route
+        assert (full["kmer_id"] == g.z["ids"]).all()
+        o = port.OracleDictionary(g.index, g.max_k)
+        k = d.k()
+        rng = np.random.default_rng(3)
+        vals = []
+        for period in range(1, 9):
+            for _ in range(40):
+                unit = rng.integers(0, 4, period)
+                vals.append(sum(int(unit[i % period]) << (2 * i) for i in range(k)))
+        ids = rng.integers(0, d.num_kmers(), 200000).astype(np.uint64)
+        km = d.access_batch(ids)
+        assert (dw.lookup_batch(km) == ids).all()                 # every sampled positive, first k-mers of strings included
+        first = d.access_batch(np.arange(0, min(d.num_kmers(), 5000), dtype=np.uint64))
+        assert (dw.lookup_batch(first) == d.lookup_batch(first)).all()
+        neg = rng.integers(0, 2 ** (2 * k), 200000, dtype=np.uint64)
+        lc = np.array(vals + [0, (1 << (2 * k)) - 1], dtype=np.uint64)
+        for arr in (neg, lc):
+            assert (dw.lookup_batch(arr) == o.lookup(arr)).all()
+        asc = g.z["read_bases"][: 40 * k].tobytes()
+        assert (dw.lookup_batch_ascii(asc) == d.lookup_batch_ascii(asc)).all()
+    finally:
+        dw.close()
