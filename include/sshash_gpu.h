@@ -138,6 +138,12 @@ SSHASH_GPU_API int sshash_gpu_lookup_batch_ascii(const sshash_gpu_dict* dict, co
 SSHASH_GPU_API int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n,
                                int check_reverse_complement, uint8_t* member, void* stream);
 
+/* Diagnostics: partitions[i] = the partition of the minimizer MPHF that k-mer i's forward minimizer
+   hashes to (external/pthash/include/partitioned_phf.hpp:145-149): the key the partition-major
+   lookup path bins queries by. */
+SSHASH_GPU_API int sshash_gpu_minimizer_partition_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n,
+                                                        uint32_t* partitions, void* stream);
+
 /* Batched dictionary::access(kmer_id, char*) (include/dictionary.hpp:71, src/dictionary.cpp:90-94),
    returning packed k-mers instead of strings.  Ids must be < num_kmers. */
 SSHASH_GPU_API int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n,

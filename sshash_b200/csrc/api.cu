@@ -283,7 +283,16 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         if (ends[i] <= ends[i - 1]) return fail(SSHASH_GPU_EFORMAT, "malformed index file (end-points not increasing)");
     if (ends.size() >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: >= 2^32 strings");
     const uint64_t U = ends.back();
+    // Directory granularity: about two blocks per string (a block then holds 0.5 end-points on average,
+    // so locate_string's scan rarely takes a step), between 2^6 and 2^16 bases.  SSHASH_GPU_LOCATE=legacy
+    // keeps round 1's fixed 2^8 blocks and 64-bit end-points (A/B switch).
+    const char* loc_env = std::getenv("SSHASH_GPU_LOCATE");
+    const bool legacy_locate = loc_env && std::strcmp(loc_env, "legacy") == 0;
     ix.dir_shift = 8;
+    if (!legacy_locate) {
+        ix.dir_shift = 6;
+        while (ix.dir_shift < 16 && (U >> ix.dir_shift) > 2 * ends.size()) ++ix.dir_shift;
+    }
     std::vector<uint32_t> dir((U >> ix.dir_shift) + 2);
     {   // dir[h] = index of the last end-point < (h << shift), 0 if none
         uint64_t j = 0;
@@ -292,6 +301,12 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
             while (j + 1 < ends.size() && ends[j + 1] < lim) ++j;
             dir[h] = (uint32_t)j;
         }
+    }
+    std::vector<uint32_t> ends32;
+    if (!legacy_locate && U < 0xffffffffull) {
+        ends32.resize(ends.size() + 2);
+        for (size_t i = 0; i != ends.size(); ++i) ends32[i] = (uint32_t)ends[i];
+        ends32[ends.size()] = ends32[ends.size() + 1] = 0xffffffffu;   // scan sentinels (> any offset)
     }
     ix.n_ends = ends.size();
     ends.push_back(~0ull); ends.push_back(~0ull);   // scan sentinels
@@ -327,11 +342,14 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     // HOT SLAB: the arrays every lookup touches (pilots, free slots, partition table, end-points and
     // their directory) live in ONE allocation so that a single L2 access-policy window can keep
     // them persistent in L2 while the cold, much larger arrays (codewords, strings) stream through.
+    // Order: the locate tables first, the pilots pool last -- when the slab is larger than the part of L2
+    // that can be set aside (human-scale indexes: > 100 MB of pilots), the persisting window covers
+    // the PREFIX that fits (configure_l2) and the pilots take the cold load policy instead.
     struct Piece { const void* src; uint64_t bytes; uint64_t off; };
-    Piece pieces[7] = {{pilots_host.data(), pilots_host.size() * 8, 0}, {free_pool.data(), free_pool.size() * 4, 0},
-                       {parts.data(), parts.size() * sizeof(DevPhfPart), 0}, {ends.data(), ends.size() * 8, 0},
-                       {dir.data(), dir.size() * 4, 0}, {wstarts.data(), wstarts.size() * 8, 0},
-                       {wdir.data(), wdir.size() * 4, 0}};
+    Piece pieces[8] = {{ends32.data(), ends32.size() * 4, 0}, {dir.data(), dir.size() * 4, 0},
+                       {parts.data(), parts.size() * sizeof(DevPhfPart), 0}, {free_pool.data(), free_pool.size() * 4, 0},
+                       {ends.data(), ends.size() * 8, 0}, {wstarts.data(), wstarts.size() * 8, 0},
+                       {wdir.data(), wdir.size() * 4, 0}, {pilots_host.data(), pilots_host.size() * 8, 0}};
     uint64_t slab_bytes = 0;
     for (auto& p : pieces) { p.off = slab_bytes; slab_bytes += (p.bytes + kPadBytes + 255) & ~255ull; }
     uint8_t* slab = nullptr;
@@ -343,15 +361,17 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         CU(cudaMemset(slab, 0, slab_bytes));
         for (auto& p : pieces) if (p.bytes) CU(cudaMemcpy(slab + p.off, p.src, p.bytes, cudaMemcpyHostToDevice));
     }
-    ix.pilots = reinterpret_cast<const uint64_t*>(slab + pieces[0].off);
-    ix.free_slots = reinterpret_cast<const uint32_t*>(slab + pieces[1].off);
+    ix.ends32 = ends32.empty() ? nullptr : reinterpret_cast<const uint32_t*>(slab + pieces[0].off);
+    ix.ends_dir = reinterpret_cast<const uint32_t*>(slab + pieces[1].off);
     const DevPhfPart* d_parts = reinterpret_cast<const DevPhfPart*>(slab + pieces[2].off);
-    ix.ends = reinterpret_cast<const uint64_t*>(slab + pieces[3].off);
-    ix.ends_dir = reinterpret_cast<const uint32_t*>(slab + pieces[4].off);
+    ix.free_slots = reinterpret_cast<const uint32_t*>(slab + pieces[3].off);
+    ix.ends = reinterpret_cast<const uint64_t*>(slab + pieces[4].off);
     ix.weight_starts = reinterpret_cast<const uint64_t*>(slab + pieces[5].off);
     ix.weight_dir = reinterpret_cast<const uint32_t*>(slab + pieces[6].off);
+    ix.pilots = reinterpret_cast<const uint64_t*>(slab + pieces[7].off);
     ix.mphf.parts = d_parts + ix.mphf.first_part_;
     for (uint32_t i = 0; i != ix.n_skew; ++i) ix.skew[i].parts = d_parts + ix.skew[i].first_part_;
+    d->ctx.hot_prefix_bytes = pieces[7].off;     // everything but the pilots
     d->ctx.hot_base = slab;
     d->ctx.hot_bytes = slab_bytes;
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
@@ -436,14 +456,20 @@ void configure_l2(sshash_gpu_dict* d) {
     const char* e = std::getenv("SSHASH_GPU_L2_PERSIST");
     const bool want = !(e && e[0] == '0');
     c.window_bytes = 0;
-    if (want && c.max_window_bytes && c.max_persist_bytes && c.hot_bytes) {
+    // Pilots that cannot stay resident next to the locate tables are loaded like the other cold arrays
+    // (evict_first, 64-byte fills) and the window shrinks to the slab's prefix (SSHASH_GPU_PILOTS_COLD=0/1 forces).
+    bool cold = c.max_persist_bytes && c.hot_bytes > c.max_persist_bytes;
+    if (const char* pc = std::getenv("SSHASH_GPU_PILOTS_COLD")) cold = pc[0] == '1';
+    d->ix.pilots_cold = cold ? 1 : 0;
+    const uint64_t span = cold ? std::max<uint64_t>(c.hot_prefix_bytes, 256) : c.hot_bytes;
+    if (want && c.max_window_bytes && c.max_persist_bytes && span) {
         size_t cur = 0;
         cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
-        const uint64_t need = std::min<uint64_t>(c.hot_bytes, c.max_persist_bytes);
+        const uint64_t need = std::min<uint64_t>(span, c.max_persist_bytes);
         if (cur < need && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, need) != cudaSuccess) cudaGetLastError();
         cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
         if (cur) {
-            c.window_bytes = std::min<uint64_t>(c.hot_bytes, c.max_window_bytes);
+            c.window_bytes = std::min<uint64_t>(span, c.max_window_bytes);
             c.hit_ratio = c.window_bytes <= cur ? 1.0f : (float)((double)cur / (double)c.window_bytes);
         }
     }
@@ -629,6 +655,20 @@ int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const uint64_t* kmer
     return run_batched(dict, kmers, 8ull * ix.kmer_words, member, 1, n, stream,
                        [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
                            return launch_lookup(ix, sms, in, false, cn, rc, nullptr, nullptr, static_cast<uint8_t*>(out), s);
+                       });
+}
+
+int sshash_gpu_minimizer_partition_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, uint32_t* partitions,
+                                         void* stream) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!kmers || !partitions) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const DeviceIndex& ix = dict->ix;
+    const LaunchCtx& sms = dict->ctx;
+    return run_batched(dict, kmers, 8ull * ix.kmer_words, partitions, 4, n, stream,
+                       [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                           return launch_minimizer_partition(ix, sms, static_cast<const uint64_t*>(in), cn, static_cast<uint32_t*>(out), s);
                        });
 }
 

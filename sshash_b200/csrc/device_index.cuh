@@ -83,6 +83,10 @@ struct DeviceIndex {
     const uint64_t* ends;
     uint64_t n_ends;
     const uint32_t* ends_dir;
+    const uint32_t* ends32;            // the same end-points as u32 when the last one is < 2^32 - 1 (else nullptr):
+                                       // locate_string reads these, half the bytes to keep L2-resident
+    uint32_t pilots_cold;              // 1 = the pilots pool does not fit the persisting part of L2: its loads
+    uint32_t pad3_;                    // take the cold policy (evict_first, 64-byte fills) like codewords / strings
     // weights (include/weights.hpp:148-153,182-187); n_weight_intervals == 0 <=> not weighted
     const uint64_t* weight_starts;     // n_weight_intervals + 1 entries (+ sentinels)
     const uint32_t* weight_dir;        // weight_dir[h] = index of the last start <= (h << weight_dir_shift)
@@ -461,7 +465,8 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
     const uint64_t h1 = h.first;
     const uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
     const uint32_t bucket = mulhi_64x32(H, num_buckets);
-    const uint64_t pilot = compact_get<true>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket);
+    const uint64_t pilot = ix.pilots_cold ? compact_get<false>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket)
+                                          : compact_get<true>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket);
     uint32_t pos = mulhi_64x32((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, table_size);
     if (pos >= num_keys) pos = ld32<true>(ix.free_slots + free_off + (pos - num_keys));
     return offset + pos;
@@ -475,6 +480,12 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
 __device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_t x, uint64_t& begin, uint64_t& end) {
     // ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none): ends[i] <= x holds
     uint64_t i = ld32<true>(ix.ends_dir + (x >> ix.dir_shift));
+    if (ix.ends32) {
+        uint32_t cur = ld32<true>(ix.ends32 + i), next = ld32<true>(ix.ends32 + i + 1);
+        while (next <= x) { cur = next; ++i; next = ld32<true>(ix.ends32 + i + 1); }
+        begin = cur; end = next;
+        return i;
+    }
     uint64_t cur = ld64<true>(ix.ends + i), next = ld64<true>(ix.ends + i + 1);
     // advance to the last end-point <= x; at most (1 << dir_shift) / k + 1 steps
     while (next <= x) { cur = next; ++i; next = ld64<true>(ix.ends + i + 1); }

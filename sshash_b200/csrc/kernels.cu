@@ -172,6 +172,25 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------------
+// diagnostics: MPHF partition of every query's forward minimizer (partitioned_phf.hpp:145-149), the key
+// the partition-major path bins by
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mphf_partition(const DevPhf& f, Hash128 h) {
+    return f.num_partitions > 1 ? (uint32_t)((((h.first ^ h.second) >> 32) * f.num_partitions) >> 32) : 0u;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBlock)
+minimizer_partition_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ kmers, uint64_t n,
+                           uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const Minimizer mi = compute_minimizer(ix, load_kmer<W>(kmers, i));
+        out[i] = mphf_partition(ix.mphf, city_hash_u64(ix.mphf, mi.value));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // open-time re-encoding of the control codewords with minimizer fingerprints: one thread per MPHF
 // slot reads the slot's codeword from the verbatim vector (still in ix.codewords, cw_fp_bits == 0),
 // follows it to the first offset of its bucket (sparse_and_skew_index.hpp:112-137), fingerprints the
@@ -1109,6 +1128,14 @@ cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
     const int grid = grid_for(n, ctx.sm_count, 8);
     if (ix.kmer_words == 1) return launch(access_kernel<1>, grid, stream, ctx, ix, ids, n, kmers_out);
     return launch(access_kernel<2>, grid, stream, ctx, ix, ids, n, kmers_out);
+}
+
+cudaError_t launch_minimizer_partition(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* kmers, uint64_t n, uint32_t* out,
+                                       cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_for(n, ctx.sm_count, 8);
+    if (ix.kmer_words == 1) return launch(minimizer_partition_kernel<1>, grid, stream, ctx, ix, kmers, n, out);
+    return launch(minimizer_partition_kernel<2>, grid, stream, ctx, ix, kmers, n, out);
 }
 
 cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* weights_out,

@@ -16,6 +16,7 @@ struct LaunchCtx {
     int sm_count = 148;
     const void* hot_base = nullptr;
     uint64_t hot_bytes = 0;
+    uint64_t hot_prefix_bytes = 0;  // the slab without its last piece (the pilots pool)
     uint64_t window_bytes = 0;      // 0 = no window
     float hit_ratio = 1.0f;
     uint64_t max_window_bytes = 0, max_persist_bytes = 0;
@@ -38,6 +39,10 @@ cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
 cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* in, bool strings, uint64_t n,
                               bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
                               cudaStream_t stream);
+
+// diagnostics: MPHF partition of each query's forward minimizer
+cudaError_t launch_minimizer_partition(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* kmers, uint64_t n, uint32_t* out,
+                                       cudaStream_t stream);
 
 // dictionary::weight for n k-mer ids (weighted indexes only)
 cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* weights_out,
