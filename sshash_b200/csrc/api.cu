@@ -227,7 +227,8 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     std::vector<uint64_t> pilots_host(pilot_words);
     uint64_t word = 0;
     std::vector<uint64_t> first_part;
-    for (auto* p : phfs) {
+    for (size_t pi = 0; pi != phfs.size(); ++pi) {
+        const PartitionedPhfView* p = phfs[pi];
         first_part.push_back(parts.size());
         for (size_t i = 0; i != p->parts.size(); ++i) {
             auto const& sp = p->parts[i];
@@ -248,6 +249,13 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
                 f.decode_elias_fano(sp.free_slots, n_free, free_pool);
                 if (free_pool.size() - before != n_free)
                     return fail(SSHASH_GPU_EFORMAT, "malformed index file (free slots)");
+                for (size_t j = before; j != free_pool.size(); ++j)      // a free slot maps to a position < num_keys
+                    if (free_pool[j] >= sp.num_keys) return fail(SSHASH_GPU_EFORMAT, "malformed index file (free slot out of range)");
+            }
+            {   // positions of this partition index the codewords (minimizer MPHF) / the skew positions
+                const uint64_t limit = pi == 0 ? f.control_codewords.size : f.skew_positions[pi - 1].size;
+                if (o.offset > limit || sp.num_keys > limit - o.offset)
+                    return fail(SSHASH_GPU_EFORMAT, "malformed index file (MPHF partition offset)");
             }
             parts.push_back(o);
         }
@@ -283,6 +291,7 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         if (ends[i] <= ends[i - 1]) return fail(SSHASH_GPU_EFORMAT, "malformed index file (end-points not increasing)");
     if (ends.size() >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: >= 2^32 strings");
     const uint64_t U = ends.back();
+    if (2 * U > f.strings.num_bits) return fail(SSHASH_GPU_EFORMAT, "malformed index file (end-points beyond the strings)");
     // Directory granularity: about two blocks per string (a block then holds 0.5 end-points on average,
     // so locate_string's scan rarely takes a step), between 2^6 and 2^16 bases.  SSHASH_GPU_LOCATE=legacy
     // keeps round 1's fixed 2^8 blocks and 64-bit end-points (A/B switch).
@@ -293,7 +302,7 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         ix.dir_shift = 6;
         while (ix.dir_shift < 16 && (U >> ix.dir_shift) > 2 * ends.size()) ++ix.dir_shift;
     }
-    std::vector<uint32_t> dir((U >> ix.dir_shift) + 2);
+    std::vector<uint32_t> dir(((f.strings.num_bits / 2) >> ix.dir_shift) + 2);   // every offset the validated buckets can hold
     {   // dir[h] = index of the last end-point < (h << shift), 0 if none
         uint64_t j = 0;
         for (uint64_t h = 0; h != dir.size(); ++h) {
@@ -376,6 +385,17 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     d->ctx.hot_bytes = slab_bytes;
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
 
+    {   // reject files whose codewords / bucket offsets point outside their arrays (kernels.cu)
+        uint32_t* d_flag = nullptr;
+        CU(cudaMalloc(reinterpret_cast<void**>(&d_flag), 4));
+        cudaError_t e = cudaMemset(d_flag, 0, 4);
+        if (e == cudaSuccess) e = launch_validate_index(ix, d->ctx, d_flag, nullptr);
+        uint32_t flag = 0;
+        if (e == cudaSuccess) e = cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_flag);
+        if (e != cudaSuccess) return cuda_fail(e, "index validation");
+        if (flag) return fail(SSHASH_GPU_EFORMAT, "malformed index file (bucket reference out of range, mask " + std::to_string(flag) + ")");
+    }
     // FINGERPRINTED CODEWORDS: the control codewords are re-encoded on the device as a compact vector
     // of width w + f whose entries carry, above the reference's w-bit codeword, an f-bit fingerprint
     // of the minimizer that owns the slot (read back from `strings` through the bucket).  A minimizer

@@ -42,7 +42,8 @@ struct Reader {
         c.data = vec(8);
         // an empty compact_vector is {0,0,0,[]}; a populated one needs width in [1,64] and enough words
         if (!fail && c.size != 0) {
-            if (c.width > 64 || c.data.n * 64 < c.size * c.width) fail = true;
+            // overflow-safe: data.n <= file_bytes / 8, so data.n * 64 cannot wrap, size * width can
+            if (c.width > 64 || (c.width && c.size > c.data.n * 64 / c.width)) fail = true;
         }
         return c;
     }
@@ -179,6 +180,7 @@ void decode_ef(const IndexFile& f, const EliasFanoView& ef, uint64_t n, std::vec
     const uint8_t* low = f.ptr(ef.low_bits.data);
     const uint64_t l = ef.low_bits.width, lmask = ef.low_bits.mask;
     const uint64_t nwords = ef.high_bits.data.n;
+    if (l && ef.low_bits.size < n) return;   // fewer low parts than values: the caller sees a short result and rejects the file
     uint64_t i = 0;
     for (uint64_t w = 0; w != nwords && i != n; ++w) {
         uint64_t word = load_word(high, w);

@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace sshash_b200 {
@@ -188,6 +189,35 @@ minimizer_partition_kernel(const __grid_constant__ DeviceIndex ix, const uint64_
         const Minimizer mi = compute_minimizer(ix, load_kmer<W>(kmers, i));
         out[i] = mphf_partition(ix.mphf, city_hash_u64(ix.mphf, mi.value));
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// open-time validation of what the lookup kernels trust without checking (a corrupted or crafted file
+// must be rejected at open, not fault later): every control codeword's bucket reference and every
+// offset stored in the bucket arrays.  Runs on the verbatim codewords (cw_fp_bits == 0).
+// flag bits: 1 singleton offset, 2 mid-load range, 4 heavy part / begin, 8 mid-load offset, 16 heavy offset
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+validate_index_kernel(const __grid_constant__ DeviceIndex ix, uint32_t* __restrict__ flag) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_bases = ix.strings_bits / 2;
+    uint32_t bad = 0;
+    for (uint64_t id = t0; id < ix.codewords.size; id += stride) {
+        uint64_t code = compact_get<false>(ix.codewords, id);
+        if ((code & 1) == 0) { if ((code >> 1) >= n_bases) bad |= 1; }
+        else if ((code & 3) == 1) {
+            code >>= 2;
+            const uint64_t size = (code & 63) + 2;
+            const uint64_t first = ix.begin_buckets_of_size[size] + (code >> 6) * size;
+            if (first + size > ix.mid_load.size || first + size < first) bad |= 2;
+        } else {
+            code >>= 2;
+            if ((code & 7) >= ix.n_skew || (code >> 3) >= ix.heavy.size) bad |= 4;
+        }
+    }
+    for (uint64_t i = t0; i < ix.mid_load.size; i += stride) if (compact_get<false>(ix.mid_load, i) >= n_bases) bad |= 8;
+    for (uint64_t i = t0; i < ix.heavy.size; i += stride) if (compact_get<false>(ix.heavy, i) >= n_bases) bad |= 16;
+    if (bad) atomicOr(flag, bad);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1161,6 +1191,12 @@ cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const
     if (e != cudaSuccess) return e;
     if ((which & 3) != 3) e = launch(reset_neighbour_slots_kernel, grid, stream, ctx, n, which, ids, full);
     return e;
+}
+
+cudaError_t launch_validate_index(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t* flag, cudaStream_t stream) {
+    const uint64_t n = std::max(ix.codewords.size, std::max(ix.mid_load.size, ix.heavy.size));
+    if (n == 0) return cudaSuccess;
+    return launch(validate_index_kernel, grid_for(n, ctx.sm_count, 8), stream, ctx, ix, flag);
 }
 
 cudaError_t launch_build_fingerprints(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t fp_bits, uint64_t* out,

@@ -48,6 +48,10 @@ cudaError_t launch_minimizer_partition(const DeviceIndex& ix, const LaunchCtx& c
 cudaError_t launch_weight(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* weights_out,
                           cudaStream_t stream);
 
+// open time: range-check every control codeword and bucket offset (verbatim codewords); *flag (zeroed
+// by the caller) receives a non-zero bit mask when the file is inconsistent
+cudaError_t launch_validate_index(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t* flag, cudaStream_t stream);
+
 // open time: re-encode ix.codewords (verbatim) into `out` (zeroed, width + fp_bits per entry) with
 // a fingerprint of each slot's minimizer above the codeword; `filter` (nullable, zeroed, 2^(32 - filter_shift)
 // words) receives the blocked Bloom filter over the same minimizers
