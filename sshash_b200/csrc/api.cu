@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <new>
+#include <stdexcept>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -44,6 +46,20 @@ int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t e__ = (call);                             \
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
+
+// No exception crosses the C ABI (include/sshash_gpu.h): every entry point runs its body through
+// guarded(), which turns std::bad_alloc into SSHASH_GPU_ENOMEM and anything else into EINVAL.
+template <typename F>
+int guarded(F&& body) noexcept {
+    try { return body(); }
+    catch (const std::bad_alloc&) { return fail(SSHASH_GPU_ENOMEM, "out of host memory"); }
+    catch (const std::exception& e) { return fail(SSHASH_GPU_EINVAL, std::string("internal error: ") + e.what()); }
+    catch (...) { return fail(SSHASH_GPU_EINVAL, "internal error: unknown exception"); }
+}
+#define SSHASH_ENTRY(name, params, args)                                   \
+    static int name##_impl params;                                         \
+    int name params { return guarded([&]() -> int { return name##_impl args; }); } \
+    static int name##_impl params
 
 constexpr uint64_t kPadBytes = 64;   // zero tail after every array (>= 2 words for funnel reads)
 
@@ -561,7 +577,7 @@ const char* sshash_gpu_build_info(void) {
 
 uint64_t sshash_gpu_launch_count(void) { return kernel_launch_count(); }
 
-int sshash_gpu_open(const char* index_path, int device, int max_k, sshash_gpu_dict** out) {
+SSHASH_ENTRY(sshash_gpu_open, (const char* index_path, int device, int max_k, sshash_gpu_dict** out), (index_path, device, max_k, out)) {
     if (!index_path || !out) return fail(SSHASH_GPU_EINVAL, "null argument");
     *out = nullptr;
     if (max_k != 0 && max_k != 31 && max_k != 63) return fail(SSHASH_GPU_EINVAL, "max_k must be 0, 31 or 63");
@@ -604,12 +620,12 @@ int sshash_gpu_open(const char* index_path, int device, int max_k, sshash_gpu_di
     return SSHASH_GPU_OK;
 }
 
-int sshash_gpu_close(sshash_gpu_dict* dict) {
+SSHASH_ENTRY(sshash_gpu_close, (sshash_gpu_dict* dict), (dict)) {
     delete dict;
     return SSHASH_GPU_OK;
 }
 
-int sshash_gpu_info(const sshash_gpu_dict* dict, sshash_gpu_info_t* out) {
+SSHASH_ENTRY(sshash_gpu_info, (const sshash_gpu_dict* dict, sshash_gpu_info_t* out), (dict, out)) {
     if (!dict || !out) return fail(SSHASH_GPU_EINVAL, "null argument");
     *out = dict->info;
     return SSHASH_GPU_OK;
@@ -653,18 +669,18 @@ static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool 
                        });
 }
 
-int sshash_gpu_lookup_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
-                            uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+SSHASH_ENTRY(sshash_gpu_lookup_batch, (const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                            uint64_t* kmer_ids, sshash_lookup_result* full, void* stream), (dict, kmers, n, check_reverse_complement, kmer_ids, full, stream)) {
     return lookup_common(dict, kmers, false, n, check_reverse_complement, kmer_ids, full, stream);
 }
 
-int sshash_gpu_lookup_batch_ascii(const sshash_gpu_dict* dict, const char* kmers, uint64_t n, int check_reverse_complement,
-                                  uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+SSHASH_ENTRY(sshash_gpu_lookup_batch_ascii, (const sshash_gpu_dict* dict, const char* kmers, uint64_t n, int check_reverse_complement,
+                                  uint64_t* kmer_ids, sshash_lookup_result* full, void* stream), (dict, kmers, n, check_reverse_complement, kmer_ids, full, stream)) {
     return lookup_common(dict, kmers, true, n, check_reverse_complement, kmer_ids, full, stream);
 }
 
-int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
-                               uint8_t* member, void* stream) {
+SSHASH_ENTRY(sshash_gpu_is_member_batch, (const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                               uint8_t* member, void* stream), (dict, kmers, n, check_reverse_complement, member, stream)) {
     int st = check_dict(dict);
     if (st) return st;
     if (n == 0) return SSHASH_GPU_OK;
@@ -678,8 +694,8 @@ int sshash_gpu_is_member_batch(const sshash_gpu_dict* dict, const uint64_t* kmer
                        });
 }
 
-int sshash_gpu_minimizer_partition_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, uint32_t* partitions,
-                                         void* stream) {
+SSHASH_ENTRY(sshash_gpu_minimizer_partition_batch, (const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, uint32_t* partitions,
+                                         void* stream), (dict, kmers, n, partitions, stream)) {
     int st = check_dict(dict);
     if (st) return st;
     if (n == 0) return SSHASH_GPU_OK;
@@ -692,8 +708,8 @@ int sshash_gpu_minimizer_partition_batch(const sshash_gpu_dict* dict, const uint
                        });
 }
 
-int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n, uint64_t* kmers_out,
-                            void* stream) {
+SSHASH_ENTRY(sshash_gpu_access_batch, (const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n, uint64_t* kmers_out,
+                            void* stream), (dict, kmer_ids, n, kmers_out, stream)) {
     int st = check_dict(dict);
     if (st) return st;
     if (n == 0) return SSHASH_GPU_OK;
@@ -706,8 +722,8 @@ int sshash_gpu_access_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_id
                        });
 }
 
-int sshash_gpu_weight_batch(const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n, uint64_t* weights_out,
-                            void* stream) {
+SSHASH_ENTRY(sshash_gpu_weight_batch, (const sshash_gpu_dict* dict, const uint64_t* kmer_ids, uint64_t n, uint64_t* weights_out,
+                            void* stream), (dict, kmer_ids, n, weights_out, stream)) {
     int st = check_dict(dict);
     if (st) return st;
     if (!dict->ix.n_weight_intervals) return fail(SSHASH_GPU_EINVAL, "the dictionary is not weighted");
@@ -765,13 +781,13 @@ static int neighbours_common(const sshash_gpu_dict* dict, const uint64_t* in, bo
     return SSHASH_GPU_OK;
 }
 
-int sshash_gpu_kmer_neighbours_batch(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
-                                     int which, uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+SSHASH_ENTRY(sshash_gpu_kmer_neighbours_batch, (const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                                     int which, uint64_t* kmer_ids, sshash_lookup_result* full, void* stream), (dict, kmers, n, check_reverse_complement, which, kmer_ids, full, stream)) {
     return neighbours_common(dict, kmers, false, n, check_reverse_complement, which, kmer_ids, full, stream);
 }
 
-int sshash_gpu_string_neighbours_batch(const sshash_gpu_dict* dict, const uint64_t* string_ids, uint64_t n,
-                                       int check_reverse_complement, uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
+SSHASH_ENTRY(sshash_gpu_string_neighbours_batch, (const sshash_gpu_dict* dict, const uint64_t* string_ids, uint64_t n,
+                                       int check_reverse_complement, uint64_t* kmer_ids, sshash_lookup_result* full, void* stream), (dict, string_ids, n, check_reverse_complement, kmer_ids, full, stream)) {
     return neighbours_common(dict, string_ids, true, n, check_reverse_complement, 3, kmer_ids, full, stream);
 }
 
@@ -798,8 +814,8 @@ static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const cha
     return SSHASH_GPU_OK;
 }
 
-int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const char* bases, const uint64_t* read_offsets, uint64_t num_reads,
-                               uint64_t* kmer_ids, sshash_streaming_report* report, void* stream) {
+SSHASH_ENTRY(sshash_gpu_streaming_batch, (const sshash_gpu_dict* dict, const char* bases, const uint64_t* read_offsets, uint64_t num_reads,
+                               uint64_t* kmer_ids, sshash_streaming_report* report, void* stream), (dict, bases, read_offsets, num_reads, kmer_ids, report, stream)) {
     int st = check_dict(dict);
     if (st) return st;
     if (!report) return fail(SSHASH_GPU_EINVAL, "null report");
@@ -1077,8 +1093,8 @@ extern "C" {
 
 // Host-side file driver: same record structure as the reference's drivers (src/query.cpp:53-108):
 // FASTA = header line + one sequence line per record, FASTQ = 4 lines per record; gz through zlib.
-int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char* filename, int multiline,
-                                         sshash_streaming_report* report) {
+SSHASH_ENTRY(sshash_gpu_streaming_query_from_file, (const sshash_gpu_dict* dict, const char* filename, int multiline,
+                                         sshash_streaming_report* report), (dict, filename, multiline, report)) {
     int st = check_dict(dict);
     if (st) return st;
     if (!filename || !report) return fail(SSHASH_GPU_EINVAL, "null argument");
@@ -1126,7 +1142,7 @@ int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char
     auto flush = [&]() -> int {
         if (offsets.size() <= 1) return SSHASH_GPU_OK;
         sshash_streaming_report r{};
-        int rc = sshash_gpu_streaming_batch(dict, bases.data(), offsets.data(), offsets.size() - 1, nullptr, &r, nullptr);
+        int rc = sshash_gpu_streaming_batch_impl(dict, bases.data(), offsets.data(), offsets.size() - 1, nullptr, &r, nullptr);
         if (rc) return rc;
         total.num_kmers += r.num_kmers; total.num_positive_kmers += r.num_positive_kmers;
         total.num_negative_kmers += r.num_negative_kmers; total.num_invalid_kmers += r.num_invalid_kmers;

@@ -29,6 +29,18 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+def _stream_for(x, stream) -> int:
+    """cudaStream_t for a call on `x`: an explicit `stream` wins; torch CUDA tensors default to torch's
+    CURRENT stream on their device (side streams are non-blocking, so the legacy default stream would
+    race the caller's producer/consumer kernels); host buffers ignore the argument (0)."""
+    if stream is not None:
+        return int(stream)
+    if _is_torch(x) and x.is_cuda:
+        import torch
+        return int(torch.cuda.current_stream(x.device).cuda_stream)
+    return 0
+
+
 def _ptr(x) -> int:
     if x is None:
         return 0
@@ -112,7 +124,7 @@ class Dictionary:
 
     # ---- lookup, include/dictionary.hpp:41-42 -------------------------------------------------
     def lookup_batch(self, kmers, check_reverse_complement: bool = True, out=None, full: bool = False,
-                     stream: int = 0):
+                     stream: Optional[int] = None):
         """Batched dictionary::lookup(Kmer, bool).  kmers: uint64 array (numpy = host, torch CUDA
         tensor = device), `words` words per k-mer.  Returns kmer ids (uint64; torch: int64 bit
         patterns) or, with full=True, a structured array of complete lookup_result records."""
@@ -125,11 +137,11 @@ class Dictionary:
             else:
                 res = np.empty(n, dtype=RESULT_DTYPE)
             check(self._lib.sshash_gpu_lookup_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), None,
-                                                    _ptr(res), stream))
+                                                    _ptr(res), _stream_for(kmers, stream)))
             return res
         ids = out if out is not None else self._alloc_like(kmers, n, np.uint64)
         check(self._lib.sshash_gpu_lookup_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(ids),
-                                                None, stream))
+                                                None, _stream_for(kmers, stream)))
         return ids
 
     def lookup_batch_ascii(self, strings: bytes, check_reverse_complement: bool = True, full: bool = False):
@@ -159,24 +171,24 @@ class Dictionary:
         return {n: int(r[n]) for n in RESULT_DTYPE.names}
 
     # ---- membership, include/dictionary.hpp:75-76 ---------------------------------------------
-    def is_member_batch(self, kmers, check_reverse_complement: bool = True, stream: int = 0):
+    def is_member_batch(self, kmers, check_reverse_complement: bool = True, stream: Optional[int] = None):
         kmers = self._prep_in(kmers)
         n = self._count(kmers)
         out = self._alloc_like(kmers, n, np.uint8)
         check(self._lib.sshash_gpu_is_member_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(out),
-                                                   stream))
+                                                   _stream_for(kmers, stream)))
         return out if _is_torch(out) else out.astype(bool)
 
     def is_member(self, kmer, check_reverse_complement: bool = True) -> bool:
         return self.lookup(kmer, check_reverse_complement)["kmer_id"] != int(INVALID)
 
     # ---- access, include/dictionary.hpp:71 ----------------------------------------------------
-    def access_batch(self, kmer_ids, stream: int = 0):
+    def access_batch(self, kmer_ids, stream: Optional[int] = None):
         kmer_ids = self._prep_in(kmer_ids)
         n = kmer_ids.numel() if _is_torch(kmer_ids) else kmer_ids.size
         shape = (n,) if self.words == 1 else (n, 2)
         out = self._alloc_like(kmer_ids, n, np.uint64, shape)
-        check(self._lib.sshash_gpu_access_batch(self._h, _ptr(kmer_ids), n, _ptr(out), stream))
+        check(self._lib.sshash_gpu_access_batch(self._h, _ptr(kmer_ids), n, _ptr(out), _stream_for(kmer_ids, stream)))
         return out
 
     def access(self, kmer_id: int) -> str:
@@ -185,12 +197,12 @@ class Dictionary:
         return uint_kmer_to_string(x, self.k())
 
     # ---- weight, include/dictionary.hpp:65-66 ---------------------------------------------------
-    def weight_batch(self, kmer_ids, stream: int = 0):
+    def weight_batch(self, kmer_ids, stream: Optional[int] = None):
         """dictionary::weight for a batch of k-mer ids (weighted dictionaries only)."""
         kmer_ids = self._prep_in(kmer_ids)
         n = kmer_ids.numel() if _is_torch(kmer_ids) else kmer_ids.size
         out = self._alloc_like(kmer_ids, n, np.uint64, (n,))
-        check(self._lib.sshash_gpu_weight_batch(self._h, _ptr(kmer_ids), n, _ptr(out), stream))
+        check(self._lib.sshash_gpu_weight_batch(self._h, _ptr(kmer_ids), n, _ptr(out), _stream_for(kmer_ids, stream)))
         return out
 
     def weight(self, kmer_id: int) -> int:
@@ -216,7 +228,7 @@ class Dictionary:
         return out
 
     # ---- streaming, include/streaming_query.hpp + src/query.cpp -------------------------------
-    def streaming_batch(self, bases, read_offsets, want_ids: bool = True, stream: int = 0):
+    def streaming_batch(self, bases, read_offsets, want_ids: bool = True, stream: Optional[int] = None):
         """Streaming membership over a batch of reads (concatenated characters + offsets).
         Returns (kmer_ids or None, report dict)."""
         if isinstance(bases, (bytes, bytearray)):
@@ -235,7 +247,7 @@ class Dictionary:
             ids = self._alloc_like(read_offsets, max(nwin, 1), np.uint64)[:nwin]
         rep = StreamingReport()
         check(self._lib.sshash_gpu_streaming_batch(self._h, _ptr(bases), _ptr(read_offsets), max(nreads, 0),
-                                                   _ptr(ids) if want_ids else None, C.byref(rep), stream))
+                                                   _ptr(ids) if want_ids else None, C.byref(rep), _stream_for(bases, stream)))
         return ids, rep.as_dict()
 
     def streaming_query_from_file(self, filename: str, multiline: bool = False) -> dict:
