@@ -76,7 +76,7 @@ def build(force: bool = False) -> str:
     src_dir = os.path.join(_HERE, "csrc")
     if force and os.path.exists(LIB_PATH):
         os.remove(LIB_PATH)
-    subprocess.check_call(["make", "-C", src_dir], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-j4", "-C", src_dir], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/sshash_gpu.h"
+#include "api_internal.hpp"
 #include "index_file.hpp"
 #include "kernels.cuh"
 
@@ -98,6 +99,8 @@ struct Workspace {
     uint64_t* d_line_start = nullptr; uint64_t ls_cap = 0;
     uint64_t* d_spans = nullptr; uint64_t spans_cap = 0;
     uint8_t* h_file[2] = {nullptr, nullptr}; uint64_t h_file_cap = 0;   // pinned
+    // partition-major lookups (binned.cu)
+    uint8_t* d_bin = nullptr; uint64_t bin_cap = 0;
 
     ~Workspace() {
         for (auto& s : slots) {
@@ -109,7 +112,7 @@ struct Workspace {
         cudaFree(d_win_offsets); cudaFree(d_block_sums);
         cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters); cudaFree(d_anchors);
         if (h_counters) cudaFreeHost(h_counters);
-        cudaFree(d_raw); cudaFree(d_tiles); cudaFree(d_line_start); cudaFree(d_spans);
+        cudaFree(d_raw); cudaFree(d_tiles); cudaFree(d_line_start); cudaFree(d_spans); cudaFree(d_bin);
         for (auto& ss : sslots) {
             cudaFree(ss.d_bases); cudaFree(ss.d_ro); cudaFree(ss.d_ids);
             if (ss.ready) cudaEventDestroy(ss.ready);
@@ -146,6 +149,8 @@ bool is_device_pointer(const void* p) {
 }
 
 }  // namespace
+
+int sshash_b200::set_last_error(int status, const std::string& msg) { return fail(status, msg); }
 
 struct sshash_gpu_dict {
     int device = 0;
@@ -479,6 +484,40 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
             ix.wide = static_cast<const ulonglong2*>(wide);
         }
     }
+    {   // PARTITION-MAJOR PATH (binned.cu): per-bin byte ranges of the pilots pool and of the codeword vector
+        BinPlan& bp = d->ctx.bins;
+        const uint64_t P = f.minimizers_mphf.parts.size();
+        bp.bin_shift = 0;
+        while ((P >> bp.bin_shift) > 1024) ++bp.bin_shift;
+        bp.n_bins = (uint32_t)((P + (1ull << bp.bin_shift) - 1) >> bp.bin_shift);
+        std::vector<BinRegion> regions(bp.n_bins);
+        const uint64_t cw_total = (ix.codewords.size * (uint64_t)ix.codewords.width + 7) / 8;
+        uint64_t pilot_bytes_total = 0;
+        for (uint32_t b = 0; b != bp.n_bins; ++b) {
+            const uint64_t p0 = (uint64_t)b << bp.bin_shift, p1 = std::min<uint64_t>(P, p0 + (1ull << bp.bin_shift)) - 1;
+            const DevPhfPart& a = parts[first_part[0] + p0];
+            const DevPhfPart& z = parts[first_part[0] + p1];
+            BinRegion r{};
+            r.pilots_off = ((uint64_t)a.pilots_word * 8) & ~15ull;     // bulk prefetches want 16-byte alignment
+            r.pilots_bytes = ((uint64_t)z.pilots_word + f.minimizers_mphf.parts[p1].pilots.data.n) * 8 - r.pilots_off;
+            const uint64_t lo = (a.offset * ix.codewords.width / 8) & ~127ull;
+            const uint64_t hi = std::min<uint64_t>(cw_total, (((z.offset + z.num_keys) * ix.codewords.width + 7) / 8 + 127) & ~127ull);
+            r.cw_off = lo;
+            r.cw_bytes = hi > lo ? hi - lo : 0;
+            regions[b] = r;
+            pilot_bytes_total += r.pilots_bytes;
+        }
+        void* d_regions = up.raw(regions.data(), regions.size() * sizeof(BinRegion));
+        if (!d_regions) return fail(SSHASH_GPU_ECUDA, up.error);
+        bp.regions = static_cast<const BinRegion*>(d_regions);
+        // Size rule (measured, profiles/r2_binned_ab.jsonl): the path pays when pilots + codewords are far
+        // beyond L2; SSHASH_GPU_BINNED=0/1 forces, SSHASH_GPU_BINNED_MIN sets the smallest batch that takes it
+        bp.enabled = pilot_bytes_total + cw_total > (256ull << 20) && P >= 4;
+        if (const char* be = std::getenv("SSHASH_GPU_BINNED")) bp.enabled = be[0] == '1';
+        bp.min_queries = env_bytes("SSHASH_GPU_BINNED_MIN", 1ull << 22);
+        if (const char* pe = std::getenv("SSHASH_GPU_BIN_PREFETCH")) bp.prefetch = pe[0] != '0';
+        bp.lookahead = (uint32_t)env_bytes("SSHASH_GPU_BIN_LOOKAHEAD", 1);
+    }
     if (!up.error.empty()) return fail(SSHASH_GPU_ECUDA, up.error);
     d->info.device_bytes = up.bytes;
     return SSHASH_GPU_OK;
@@ -494,7 +533,10 @@ void configure_l2(sshash_gpu_dict* d) {
     c.window_bytes = 0;
     // Pilots that cannot stay resident next to the locate tables are loaded like the other cold arrays
     // (evict_first, 64-byte fills) and the window shrinks to the slab's prefix (SSHASH_GPU_PILOTS_COLD=0/1 forces).
-    bool cold = c.max_persist_bytes && c.hot_bytes > c.max_persist_bytes;
+    // Measured on the 2.5e9-k-mer index (profiles/r2_exp_locality_v1.jsonl): a partially resident pilots pool
+    // (evict_last, window over the whole slab with hitRatio = persisting / window) beats the cold policy
+    // (13.5 vs 12.8 G lookups/s forward, 13.3 vs 10.7 negative), so cold pilots are opt-in only.
+    bool cold = false;
     if (const char* pc = std::getenv("SSHASH_GPU_PILOTS_COLD")) cold = pc[0] == '1';
     d->ix.pilots_cold = cold ? 1 : 0;
     const uint64_t span = cold ? std::max<uint64_t>(c.hot_prefix_bytes, 256) : c.hot_bytes;
@@ -508,6 +550,13 @@ void configure_l2(sshash_gpu_dict* d) {
             c.window_bytes = std::min<uint64_t>(span, c.max_window_bytes);
             c.hit_ratio = c.window_bytes <= cur ? 1.0f : (float)((double)cur / (double)c.window_bytes);
         }
+    }
+    {   // window of the partition-major path: the slab's prefix (locate tables, free slots), never the pilots
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        const uint64_t prefix = std::min<uint64_t>(c.hot_prefix_bytes, c.max_window_bytes);
+        c.bins.window_bytes = (want && cur && prefix) ? prefix : 0;
+        c.bins.hit_ratio = prefix <= cur ? 1.0f : (float)((double)cur / (double)prefix);
     }
     if (const char* g = std::getenv("SSHASH_GPU_L2_FETCH")) {
         size_t v = (size_t)std::atoi(g);
@@ -631,6 +680,30 @@ SSHASH_ENTRY(sshash_gpu_info, (const sshash_gpu_dict* dict, sshash_gpu_info_t* o
     return SSHASH_GPU_OK;
 }
 
+// Device-resident batch through the partition-major path (binned.cu), in launches of at most
+// binned_max_batch() queries.  The scratch belongs to a pooled workspace, so the call waits for the
+// stream before handing it back (the direct kernel stays fully asynchronous).
+static bool use_binned(const sshash_gpu_dict* dict, const void* in, const void* out, uint64_t n) {
+    const BinPlan& bp = dict->ctx.bins;
+    return bp.enabled && bp.n_bins && n >= bp.min_queries && is_device_pointer(in) && is_device_pointer(out);
+}
+
+static int lookup_binned_device(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, bool check_rc, uint64_t* ids,
+                                uint32_t* ids32, uint8_t* member, void* stream) {
+    const DeviceIndex& ix = dict->ix;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    WorkspaceLease ws(dict);
+    const uint64_t step = std::min<uint64_t>(n, binned_max_batch());
+    CU(ensure(ws->d_bin, ws->bin_cap, binned_scratch_bytes(ix, dict->ctx, step)));
+    for (uint64_t off = 0; off < n; off += step) {
+        const uint64_t cn = std::min(step, n - off);
+        CU(launch_lookup_binned(ix, dict->ctx, kmers + off * ix.kmer_words, cn, check_rc, ids ? ids + off : nullptr,
+                                ids32 ? ids32 + off : nullptr, member ? member + off : nullptr, ws->d_bin, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return SSHASH_GPU_OK;
+}
+
 static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool ascii, uint64_t n, int check_rc,
                          uint64_t* kmer_ids, sshash_lookup_result* full, void* stream) {
     int st = check_dict(dict);
@@ -663,6 +736,8 @@ static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool 
                            [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
                                return launch_lookup(ix, sms, in, ascii, cn, rc, nullptr, static_cast<sshash_lookup_result*>(out), nullptr, s);
                            });
+    if (!ascii && use_binned(dict, queries, kmer_ids, n))
+        return lookup_binned_device(dict, static_cast<const uint64_t*>(queries), n, rc, kmer_ids, nullptr, nullptr, stream);
     return run_batched(dict, queries, in_elem, kmer_ids, 8, n, stream,
                        [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
                            return launch_lookup(ix, sms, in, ascii, cn, rc, static_cast<uint64_t*>(out), nullptr, nullptr, s);
@@ -688,6 +763,7 @@ SSHASH_ENTRY(sshash_gpu_is_member_batch, (const sshash_gpu_dict* dict, const uin
     const DeviceIndex& ix = dict->ix;
     const LaunchCtx& sms = dict->ctx;
     const bool rc = check_reverse_complement != 0;
+    if (use_binned(dict, kmers, member, n)) return lookup_binned_device(dict, kmers, n, rc, nullptr, nullptr, member, stream);
     return run_batched(dict, kmers, 8ull * ix.kmer_words, member, 1, n, stream,
                        [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
                            return launch_lookup(ix, sms, in, false, cn, rc, nullptr, nullptr, static_cast<uint8_t*>(out), s);

@@ -152,34 +152,40 @@ __device__ __forceinline__ uint64_t low_mask(uint32_t bits) {  // bits in [0,64]
 //        are loaded evict_first so that they do not push the hot arrays out.
 // createpolicy with constant operands folds into a uniform descriptor register (no per-thread cost).
 // ------------------------------------------------------------------------------------------------
-template <bool HOT>
+// POLICY: 0 = COLD, 1 = HOT (the historical bool spelling still works: false / true), 2 = NORMAL: no hint, full
+// 128-byte fills -- used by the partition-major path for pilots and codewords, which it visits one
+// partition at a time so that they are L2 hits by schedule (binned.cu).
+constexpr int kCold = 0, kHot = 1, kNormal = 2;
+template <int POLICY>
 __device__ __forceinline__ uint64_t l2_policy() {
     uint64_t p;
-    if (HOT) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    if (POLICY == kHot) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     else asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 // COLD loads additionally carry .L2::64B: measured on B200 (tools/micro/gather.cu) a default load
 // that misses L2 pulls 128 B from HBM, with .L2::64B it pulls 64 B -- the minimum -- which halves
 // the DRAM traffic of the random codeword / strings accesses.
-template <bool HOT>
+template <int POLICY>
 __device__ __forceinline__ uint64_t ld64(const uint64_t* __restrict__ p) {
     uint64_t v;
-    if (HOT) asm("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<true>()));
-    else asm("ld.global.nc.L2::cache_hint.L2::64B.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<false>()));
+    if (POLICY == kHot) asm("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<kHot>()));
+    else if (POLICY == kNormal) asm("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else asm("ld.global.nc.L2::cache_hint.L2::64B.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<kCold>()));
     return v;
 }
-template <bool HOT>
+template <int POLICY>
 __device__ __forceinline__ uint32_t ld32(const uint32_t* __restrict__ p) {
     uint32_t v;
-    if (HOT) asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<true>()));
-    else asm("ld.global.nc.L2::cache_hint.L2::64B.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<false>()));
+    if (POLICY == kHot) asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<kHot>()));
+    else if (POLICY == kNormal) asm("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm("ld.global.nc.L2::cache_hint.L2::64B.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_policy<kCold>()));
     return v;
 }
 
 __device__ __forceinline__ ulonglong2 ld128_cold(const ulonglong2* __restrict__ p) {
     ulonglong2 v;
-    asm("ld.global.nc.L2::cache_hint.L2::64B.v2.b64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_policy<false>()));
+    asm("ld.global.nc.L2::cache_hint.L2::64B.v2.b64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_policy<kCold>()));
     return v;
 }
 
@@ -258,7 +264,7 @@ __device__ __forceinline__ uint64_t read_mmer(const DeviceIndex& ix, uint64_t ba
 
 // compact_vector::access, compact_vector.hpp:253-260 (two aligned word loads instead of one
 // unaligned 8-byte load)
-template <bool HOT>
+template <int HOT>
 __device__ __forceinline__ uint64_t compact_get(const uint64_t* __restrict__ data, uint32_t width, uint64_t mask, uint64_t i) {
     uint64_t pos = i * width, w = pos >> 6;
     uint32_t s = (uint32_t)pos & 63u;
@@ -266,7 +272,7 @@ __device__ __forceinline__ uint64_t compact_get(const uint64_t* __restrict__ dat
     if (s + width > 64) v |= ld64<HOT>(data + w + 1) << (64 - s);
     return v & mask;
 }
-template <bool HOT>
+template <int HOT>
 __device__ __forceinline__ uint64_t compact_get(const DevCompact& c, uint64_t i) {
     return compact_get<HOT>(c.data, c.width, c.mask, i);
 }
@@ -455,9 +461,14 @@ __device__ __forceinline__ uint32_t mulhi_64x32(uint64_t x, uint32_t y) {
     return (uint32_t)(((x >> 32) * y + (lo >> 32)) >> 32);
 }
 
+// partitioned_phf::position's partition choice, partitioned_phf.hpp:145-149
+__device__ __forceinline__ uint32_t mphf_partition(const DevPhf& f, Hash128 h) {
+    return f.num_partitions > 1 ? (uint32_t)((((h.first ^ h.second) >> 32) * f.num_partitions) >> 32) : 0u;
+}
+
+template <bool BINNED = false>
 __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const DevPhf& f, Hash128 h) {
-    uint64_t part = 0;
-    if (f.num_partitions > 1) part = (((h.first ^ h.second) >> 32) * f.num_partitions) >> 32;
+    const uint64_t part = mphf_partition(f, h);
     const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(f.parts + part);
     const uint4 a = __ldg(rec), b = __ldg(rec + 1);
     const uint64_t offset = ((uint64_t)a.y << 32) | a.x;
@@ -465,8 +476,10 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
     const uint64_t h1 = h.first;
     const uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
     const uint32_t bucket = mulhi_64x32(H, num_buckets);
-    const uint64_t pilot = ix.pilots_cold ? compact_get<false>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket)
-                                          : compact_get<true>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket);
+    const uint64_t* pw = ix.pilots + pilots_word;
+    const uint64_t pilot = BINNED ? compact_get<kNormal>(pw, pilot_width, low_mask(pilot_width), bucket)
+                           : ix.pilots_cold ? compact_get<kCold>(pw, pilot_width, low_mask(pilot_width), bucket)
+                                            : compact_get<kHot>(pw, pilot_width, low_mask(pilot_width), bucket);
     uint32_t pos = mulhi_64x32((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, table_size);
     if (pos >= num_keys) pos = ld32<true>(ix.free_slots + free_off + (pos - num_keys));
     return offset + pos;
@@ -539,7 +552,7 @@ __device__ __forceinline__ void filter_slot(uint32_t key32, uint32_t shift, uint
 // USE_FP: reject a minimizer whose slot belongs to a different minimizer (returns 0 = no bucket).
 // Only the ids-only paths may use it: a full lookup_result needs the bucket type of the (wrong)
 // slot to reproduce minimizer_found (spss.hpp:51-65).
-template <int W, bool USE_FP, bool USE_FILTER = false>
+template <int W, bool USE_FP, bool USE_FILTER = false, bool BINNED = false>
 __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t minimizer, Kmer<W> skew_key,
                                               uint64_t& first, bool& heavy) {
     uint32_t fp = 0;
@@ -552,10 +565,11 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
         }
         fp = fingerprint_of_key(ix, key32);                   // before the loads: only 32 bits stay live across them
     }
-    uint64_t id = phf_position(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
+    uint64_t id = phf_position<BINNED>(ix, ix.mphf, city_hash_u64(ix.mphf, minimizer));   // minimizers_control_map.hpp:36-39
     // entries are exactly 32 bits wide whenever the reference's codeword has <= 24 bits (api.cu)
-    uint64_t code = ix.codewords.width == 32 ? (uint64_t)ld32<false>(reinterpret_cast<const uint32_t*>(ix.codewords.data) + id)
-                                             : compact_get<false>(ix.codewords, id);
+    constexpr int CW = BINNED ? kNormal : kCold;
+    uint64_t code = ix.codewords.width == 32 ? (uint64_t)ld32<CW>(reinterpret_cast<const uint32_t*>(ix.codewords.data) + id)
+                                             : compact_get<CW>(ix.codewords, id);
     heavy = false;
     if (ix.cw_fp_bits) {
         if (USE_FP && (uint32_t)(code >> ix.cw_code_bits) != fp) return 0;
@@ -589,11 +603,11 @@ __device__ __forceinline__ uint32_t bucket_of(const DeviceIndex& ix, uint64_t mi
 // FULL = also produce minimizer_found exactly (needs the m-mer check of spss.hpp:46-65); without
 // it the k-mer comparison alone decides, which yields the same ids (a k-mer match implies the
 // m-mer match because the minimizer is a substring of the k-mer at pos_in_kmer).
-template <int W, bool FULL, bool FILTER = false>
+template <int W, bool FULL, bool FILTER = false, bool BINNED = false>
 __device__ __forceinline__ bool lookup_regular_with(const DeviceIndex& ix, Kmer<W> x, Minimizer mi, LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     uint64_t first; bool heavy;
-    uint32_t n = bucket_of<W, !FULL, FILTER>(ix, mi.value, x, first, heavy);
+    uint32_t n = bucket_of<W, !FULL, FILTER, BINNED>(ix, mi.value, x, first, heavy);
     if (!FULL && n == 0) { result_clear(res, false); return false; }
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {
@@ -637,13 +651,13 @@ __device__ __forceinline__ bool lookup_regular(const DeviceIndex& ix, Kmer<W> x,
 
 // Canonical pass: dictionary::lookup_canonical(kmer, kmer_rc, mini_info) (src/dictionary.cpp:44-56)
 // + spss::lookup_canonical (spss.hpp:75-112, _lookup_canonical :237-247, __lookup_canonical :249-275)
-template <int W, bool FULL, bool FILTER = false>
+template <int W, bool FULL, bool FILTER = false, bool BINNED = false>
 __device__ __forceinline__ bool lookup_canonical_with(const DeviceIndex& ix, Kmer<W> x, Kmer<W> xr, Minimizer mi,
                                                       LookupResult& res) {
     const uint32_t k = ix.k, m = ix.m;
     Kmer<W> canon = kmer_lt(x, xr) ? x : xr;            // std::min(uint_kmer, uint_kmer_rc), dictionary.cpp:53
     uint64_t first; bool heavy;
-    uint32_t n = bucket_of<W, !FULL, FILTER>(ix, mi.value, canon, first, heavy);
+    uint32_t n = bucket_of<W, !FULL, FILTER, BINNED>(ix, mi.value, canon, first, heavy);
     if (!FULL && n == 0) { result_clear(res, false); return false; }
     uint64_t off0 = (n == 1) ? first : compact_get<false>(ix.mid_load, first);
     if (FULL) {

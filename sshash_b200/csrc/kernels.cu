@@ -6,6 +6,7 @@
 // dependent loads, and the only way to cover ~600-800 ns of HBM latency per link is to keep tens
 // of thousands of independent chains in flight (148 SMs x up to 2048 threads).
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_runtime.h>
 
@@ -16,7 +17,6 @@ namespace sshash_b200 {
 
 namespace {
 
-constexpr int kBlock = 256;
 // 6 resident CTAs/SM (<= 40 registers, 75 % occupancy): measured best on B200 for both the L2-resident
 // and the HBM-resident case (sweep over 3/4/5/6/8 in profiles/r1_notes.md)
 #ifndef SSHASH_LOOKUP_MINB
@@ -30,22 +30,6 @@ constexpr int kLookupMinBlocks = SSHASH_LOOKUP_MINB;
 #define SSHASH_WIDE_CANON_MINB 6
 #endif
 constexpr int kLookupMinBlocksWideCanon = SSHASH_WIDE_CANON_MINB;
-
-template <int W>
-__device__ __forceinline__ Kmer<W> load_kmer(const uint64_t* __restrict__ kmers, uint64_t i);
-template <>
-__device__ __forceinline__ Kmer<1> load_kmer<1>(const uint64_t* __restrict__ kmers, uint64_t i) {
-    return {__ldcs(kmers + i)};
-}
-template <>
-__device__ __forceinline__ Kmer<2> load_kmer<2>(const uint64_t* __restrict__ kmers, uint64_t i) {
-    ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(kmers) + i);
-    return {v.x, v.y};
-}
-__device__ __forceinline__ void store_kmer(uint64_t* out, uint64_t i, Kmer<1> x) { __stcs(out + i, x.lo); }
-__device__ __forceinline__ void store_kmer(uint64_t* out, uint64_t i, Kmer<2> x) {
-    __stcs(reinterpret_cast<ulonglong2*>(out) + i, make_ulonglong2(x.lo, x.hi));
-}
 
 __device__ __forceinline__ void store_full(sshash_lookup_result* full, uint64_t i, const LookupResult& r) {
     // 64-byte record written as four 16-byte streaming stores
@@ -176,10 +160,6 @@ lookup_kernel(const __grid_constant__ DeviceIndex ix, const void* __restrict__ q
 // diagnostics: MPHF partition of every query's forward minimizer (partitioned_phf.hpp:145-149), the key
 // the partition-major path bins by
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mphf_partition(const DevPhf& f, Hash128 h) {
-    return f.num_partitions > 1 ? (uint32_t)((((h.first ^ h.second) >> 32) * f.num_partitions) >> 32) : 0u;
-}
-
 template <int W>
 __global__ void __launch_bounds__(kBlock)
 minimizer_partition_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ kmers, uint64_t n,
@@ -1082,42 +1062,9 @@ read_spans_kernel(const uint64_t* __restrict__ line_start, uint64_t num_records,
     }
 }
 
-std::atomic<uint64_t> g_launches{0};
-
-// every kernel of the lookup path is launched through here: <<<grid, kBlock>>> plus the L2
-// access-policy window that keeps the hot slab (pilots, end-points, ...) persistent in L2
-template <typename... KArgs, typename... Args>
-cudaError_t launch(void (*kernel)(KArgs...), int grid, cudaStream_t stream, const LaunchCtx& ctx, Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kBlock);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    cfg.attrs = attr;
-    cfg.numAttrs = 0;
-    if (ctx.window_bytes) {
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(ctx.hot_base);
-        attr[0].val.accessPolicyWindow.num_bytes = ctx.window_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = ctx.hit_ratio;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cfg.numAttrs = 1;
-    }
-    g_launches.fetch_add(1);
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
-inline int grid_for(uint64_t n, int sm_count, int blocks_per_sm) {
-    uint64_t need = (n + kBlock - 1) / kBlock;
-    uint64_t cap = (uint64_t)sm_count * blocks_per_sm;
-    if (need < 1) need = 1;
-    return (int)(need < cap ? need : cap);
-}
-
 }  // namespace
 
+std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launch_count() { return g_launches.load(); }
 
 cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const void* queries, bool ascii, uint64_t n, bool check_rc,

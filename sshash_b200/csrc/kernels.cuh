@@ -11,6 +11,23 @@
 
 namespace sshash_b200 {
 
+// Partition-major path (binned.cu): what one bin (= 2^bin_shift consecutive partitions of the minimizer
+// MPHF) touches -- byte ranges inside the pilots pool and the control-codeword vector, 16-byte aligned
+struct BinRegion {
+    uint64_t pilots_off, pilots_bytes;
+    uint64_t cw_off, cw_bytes;
+};
+struct BinPlan {
+    uint32_t n_bins = 0, bin_shift = 0;   // n_bins == 0: the path is unavailable for this index
+    const BinRegion* regions = nullptr;   // device array, n_bins entries
+    bool enabled = false;                 // chosen at open (SSHASH_GPU_BINNED=0/1 overrides the size rule)
+    bool prefetch = true;                 // bulk L2 prefetch of the next bins' regions
+    uint32_t lookahead = 1;               // how many bins ahead the prefetch runs
+    uint64_t min_queries = 1ull << 22;    // smaller device-resident batches take the direct kernel
+    uint64_t window_bytes = 0;            // L2 window of this path: the locate tables only
+    float hit_ratio = 1.0f;
+};
+
 // per-dictionary launch facts: grid sizing and the L2 access-policy window over the hot slab
 struct LaunchCtx {
     int sm_count = 148;
@@ -20,6 +37,7 @@ struct LaunchCtx {
     uint64_t window_bytes = 0;      // 0 = no window
     float hit_ratio = 1.0f;
     uint64_t max_window_bytes = 0, max_persist_bytes = 0;
+    BinPlan bins;
 };
 
 // number of kernels launched by this library since it was loaded (bench.py's `gpu_launches`)
@@ -39,6 +57,14 @@ cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uin
 cudaError_t launch_neighbours(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* in, bool strings, uint64_t n,
                               bool check_rc, int which, uint64_t* expanded, uint64_t* ids, sshash_lookup_result* full,
                               cudaStream_t stream);
+
+// Partition-major batched lookup (binned.cu): ids (u64), ids32 (u32, UINT32_MAX = not found) or member
+// bytes for n <= binned_max_batch() packed k-mers, all DEVICE pointers; `scratch` holds
+// binned_scratch_bytes(ix, ctx, n) bytes.  Fully asynchronous on `stream`.
+uint64_t binned_max_batch();
+uint64_t binned_scratch_bytes(const DeviceIndex& ix, const LaunchCtx& ctx, uint64_t n);
+cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* queries, uint64_t n, bool check_rc,
+                                 uint64_t* ids, uint32_t* ids32, uint8_t* member, void* scratch, cudaStream_t stream);
 
 // diagnostics: MPHF partition of each query's forward minimizer
 cudaError_t launch_minimizer_partition(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* kmers, uint64_t n, uint32_t* out,

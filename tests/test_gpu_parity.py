@@ -455,6 +455,85 @@ def test_multi_partition_index_vs_oracle(tmp_path):
     d.close()
 
 
+def _open_with_env(path, env, **kw):
+    """Dictionary opened under a set of library environment switches (they are read at open time)."""
+    import sshash_b200
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return sshash_b200.Dictionary(path, **kw)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+BINNED_ON = {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BINNED_MIN": "1"}
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_binned_path_gives_the_reference_ids(name):
+    """Partition-major path (binned.cu) forced on for every golden index (one bin there: the
+    multisplit, both rounds, the canonical tie and the un-permute still run): device-resident
+    lookups and membership equal the reference's golden ids, with and without the rc pass."""
+    import torch
+    g = golden(name)
+    d = _open_with_env(g.index, BINNED_ON, device=0, max_k=g.max_k)
+    q = torch.from_numpy(g.z["queries"].view(np.int64)).cuda()
+    ids = d.lookup_batch(q)
+    assert (ids.cpu().numpy().view(np.uint64) == g.z["ids"]).all()
+    ids = d.lookup_batch(q, check_reverse_complement=False)
+    assert (ids.cpu().numpy().view(np.uint64) == g.z["ids_norc"]).all()
+    mem = d.is_member_batch(q)
+    assert (mem.cpu().numpy().astype(bool) == (g.z["ids"] != INVALID)).all()
+    d.close()
+
+
+def test_binned_path_multi_partition_multi_range(tmp_path):
+    """Several MPHF partitions (bins) and several 2^20-query output ranges: 2.6e6 device-resident
+    queries (positives, half reverse-complemented, interleaved with random negatives) through the
+    partition-major path against the direct kernel and, on a sample, the C oracle."""
+    import torch
+    from oracle import port, ref
+    if not ref.available(31):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    fa = tmp_path / "synth.fa"
+    with open(fa, "w") as f:
+        for i in range(13000):
+            f.write(">%d\n%s\n" % (i, "".join("ACGT"[c] for c in rng.integers(0, 4, 3000))))
+    for canonical in (False, True):
+        idx = str(tmp_path / ("synth%d.sshash" % canonical))
+        ref.build(str(fa), 31, 14, idx, canonical=canonical, threads=min(16, os.cpu_count() or 1), tmp_dir=str(tmp_path))
+        direct = _open_with_env(idx, {"SSHASH_GPU_BINNED": "0"})
+        binned = _open_with_env(idx, BINNED_ON)
+        assert binned.info["mphf_partitions"] >= 2
+        n = 2_600_001
+        ids = rng.integers(0, direct.num_kmers(), n).astype(np.uint64)
+        pos = direct.access_batch(ids)
+        o = port.OracleDictionary(idx)
+        from bench import rc_packed_torch
+        q = pos.copy()
+        q[1::4] = rc_packed_torch(torch.from_numpy(pos[1::4].view(np.int64).copy()), 31).numpy().view(np.uint64)
+        q[2::4] = rng.integers(0, 2**62, q[2::4].size).astype(np.uint64)      # negatives
+        q[3::4] = q[0::4][: q[3::4].size]                                      # duplicates of other queries
+        qd = torch.from_numpy(q.view(np.int64)).cuda()
+        for rc in (True, False):
+            a = direct.lookup_batch(qd, check_reverse_complement=rc)
+            b = binned.lookup_batch(qd, check_reverse_complement=rc)
+            torch.cuda.synchronize()
+            assert torch.equal(a, b)
+            assert torch.equal(direct.is_member_batch(qd, check_reverse_complement=rc), binned.is_member_batch(qd, check_reverse_complement=rc))
+        got = binned.lookup_batch(qd).cpu().numpy().view(np.uint64)
+        assert (got[0::4] == ids[0::4]).all()
+        m = 200000
+        assert (got[:m] == o.lookup(q[:m])).all()
+        direct.close()
+        binned.close()
+
+
 def test_sharded_lookup_with_peer_store_gather_two_gpus():
     """N > 1: every rank's lookup kernel stores its ids straight into rank 0's gathered vector through
     NVLink peer stores (sshash_b200.sharded, mode "peer"); rank 0 checks every slice against the

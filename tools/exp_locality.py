@@ -20,11 +20,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 VARIANTS = {
-    "r1_layout": {"SSHASH_GPU_LOCATE": "legacy", "SSHASH_GPU_PILOTS_COLD": "0"},
-    "compact_locate": {"SSHASH_GPU_PILOTS_COLD": "0"},
-    "compact_locate+pilots_cold": {"SSHASH_GPU_PILOTS_COLD": "1"},
+    "r1_layout": {"SSHASH_GPU_LOCATE": "legacy", "SSHASH_GPU_BINNED": "0"},
+    "direct": {"SSHASH_GPU_BINNED": "0"},
+    "direct+pilots_cold": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "1"},
+    "binned": {"SSHASH_GPU_BINNED": "1"},
+    "binned_noprefetch": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_PREFETCH": "0"},
+    "binned_lookahead2": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_LOOKAHEAD": "2"},
     "default": {},
 }
+ENV_KEYS = ("SSHASH_GPU_LOCATE", "SSHASH_GPU_PILOTS_COLD", "SSHASH_GPU_BINNED", "SSHASH_GPU_BIN_PREFETCH", "SSHASH_GPU_BIN_LOOKAHEAD")
 
 
 def main():
@@ -35,7 +39,8 @@ def main():
     ap.add_argument("-m", type=int, default=21)
     ap.add_argument("--queries", type=int, default=100_000_000)
     ap.add_argument("--workdir", default="/tmp/ix")
-    ap.add_argument("--variants", default=",".join(VARIANTS))
+    ap.add_argument("--variants", default="direct,binned,binned_noprefetch,binned_lookahead2")
+    ap.add_argument("--no-sorted", action="store_true", help="skip the runs on queries pre-sorted by partition")
     a = ap.parse_args()
     import torch
     import sshash_b200
@@ -59,7 +64,7 @@ def main():
     queries = None
     for name in a.variants.split(","):
         env = VARIANTS[name]
-        saved = {k: os.environ.get(k) for k in ("SSHASH_GPU_LOCATE", "SSHASH_GPU_PILOTS_COLD")}
+        saved = {k: os.environ.get(k) for k in ENV_KEYS}
         for k in saved:
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -94,12 +99,17 @@ def main():
             ms = time_lookup(d, q, out)
             if qname != "neg":
                 assert torch.equal(out, ids)
-            ms_sorted = time_lookup(d, qs, out)
-            if qname != "neg":
-                assert torch.equal(out, ids[order])
-            res[qname] = {"G_lookups_per_s": n / ms / 1e6, "roofline_frac": b_alg * n / ms * 1e3 / 1e9 / peak,
-                          "sorted_by_partition_G_lookups_per_s": n / ms_sorted / 1e6,
-                          "sorted_roofline_frac": b_alg * n / ms_sorted * 1e3 / 1e9 / peak}
+            else:
+                found = int((out != -1).sum())
+            res[qname] = {"ms": ms, "G_lookups_per_s": n / ms / 1e6, "roofline_frac": b_alg * n / ms * 1e3 / 1e9 / peak}
+            if qname == "neg":
+                res[qname]["found"] = found
+            if not a.no_sorted and "BINNED" not in str(env.get("SSHASH_GPU_BINNED", "0")) and env.get("SSHASH_GPU_BINNED") != "1":
+                ms_sorted = time_lookup(d, qs, out)
+                if qname != "neg":
+                    assert torch.equal(out, ids[order])
+                res[qname].update({"sorted_by_partition_G_lookups_per_s": n / ms_sorted / 1e6,
+                                   "sorted_roofline_frac": b_alg * n / ms_sorted * 1e3 / 1e9 / peak})
         print(json.dumps(res), flush=True)
         d.close()
         del out
