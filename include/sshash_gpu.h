@@ -13,7 +13,10 @@
  *   - every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the
  *     dictionary's GPU; the library detects which (cudaPointerGetAttributes).  Host buffers are
  *     streamed through the GPU in chunks with copies overlapped with the kernels; device buffers
- *     are used in place;
+ *     are used in place (for lookup / membership / access / weight a pointer into ANOTHER GPU's
+ *     memory is accepted too and staged like a host buffer, peer-to-peer when peer access is on).
+ *     Device buffers of packed k-mers must be 8-byte aligned, 16-byte aligned when max_k = 63 or when
+ *     full lookup_result records are requested (128-bit loads / stores);
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  With device
  *     buffers the call is asynchronous on that stream; with host buffers `stream` is ignored, the
  *     library pipelines the batch on its own streams and returns when the outputs are complete;
@@ -125,6 +128,14 @@ SSHASH_GPU_API int sshash_gpu_lookup_batch(const sshash_gpu_dict* dict, const ui
                             sshash_lookup_result* full, void* stream);
 
 /*
+ * The same lookup with 32-bit ids, for dictionaries with fewer than 2^32 - 1 k-mers (every index of
+ * up to ~4.29e9 k-mers): kmer_ids32[i] = (uint32_t)lookup(...).kmer_id, "not found" = UINT32_MAX.
+ * Halves the id bytes that cross PCIe / NVLink; SSHASH_GPU_EINVAL when the dictionary is larger.
+ */
+SSHASH_GPU_API int sshash_gpu_lookup_batch_u32(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n,
+                                               int check_reverse_complement, uint32_t* kmer_ids32, void* stream);
+
+/*
  * Batched dictionary::lookup(char const* string_kmer, bool) (include/dictionary.hpp:41,
  * src/dictionary.cpp:58-63): n strings of exactly k characters, back to back, no terminators,
  * no validation (non-ACGT bytes alias through (c>>1)&3 exactly as in the reference).
@@ -188,6 +199,39 @@ SSHASH_GPU_API int sshash_gpu_streaming_batch(const sshash_gpu_dict* dict, const
    src/query.cpp:118-175): .fa/.fasta/.fq/.fastq, optionally .gz. */
 SSHASH_GPU_API int sshash_gpu_streaming_query_from_file(const sshash_gpu_dict* dict, const char* filename,
                                          int multiline, sshash_streaming_report* report);
+
+/*
+ * Several GPUs of one box behind one handle (BASELINE.json configs[4]).  The reference
+ * has one `dictionary` object per process (include/dictionary.hpp:10-181) and shards nothing; here
+ * the index is REPLICATED on every listed GPU and each batch is SHARDED by query in contiguous
+ * slices, slice j on devices[j] (sizes differ by at most one; results keep the query order).  One
+ * host thread per GPU drives its slice through the single-device entry points above:
+ *   - host buffers: every GPU moves its own slice over its own PCIe link, the ids land in the
+ *     caller's array -- no inter-GPU traffic at all;
+ *   - device buffers (on any GPU of the box): the owning GPU works in place, the others stage their
+ *     slices with peer-to-peer copy-engine transfers over NVLink, so all ids arrive in the owner's
+ *     vector (the "gather of ids" of configs[4]) without using SMs for communication.
+ * devices == NULL: ordinals 0 .. n_devices-1; n_devices <= 0: every visible GPU.  Calls return when
+ * the outputs are complete.  sshash_gpu_multi_dict(m, i) exposes the i-th replica for the
+ * single-device calls (access, weight, neighbours, file streaming ...).
+ */
+typedef struct sshash_gpu_multi sshash_gpu_multi;
+SSHASH_GPU_API int sshash_gpu_multi_open(const char* index_path, const int* devices, int n_devices, int max_k,
+                                         sshash_gpu_multi** out);
+SSHASH_GPU_API int sshash_gpu_multi_close(sshash_gpu_multi* m);
+SSHASH_GPU_API int sshash_gpu_multi_num_devices(const sshash_gpu_multi* m);
+SSHASH_GPU_API const sshash_gpu_dict* sshash_gpu_multi_dict(const sshash_gpu_multi* m, int i);
+/* dictionary::lookup / is_member over a sharded batch (src/dictionary.cpp:64-88) */
+SSHASH_GPU_API int sshash_gpu_multi_lookup_batch(const sshash_gpu_multi* m, const uint64_t* kmers, uint64_t n,
+                                                 int check_reverse_complement, uint64_t* kmer_ids);
+SSHASH_GPU_API int sshash_gpu_multi_lookup_batch_u32(const sshash_gpu_multi* m, const uint64_t* kmers, uint64_t n,
+                                                     int check_reverse_complement, uint32_t* kmer_ids32);
+SSHASH_GPU_API int sshash_gpu_multi_is_member_batch(const sshash_gpu_multi* m, const uint64_t* kmers, uint64_t n,
+                                                    int check_reverse_complement, uint8_t* member);
+/* streaming membership (include/streaming_query.hpp:56-115) over HOST reads sharded by read; the
+   six counters are per-read sums, so the shards' reports add up */
+SSHASH_GPU_API int sshash_gpu_multi_streaming_batch(const sshash_gpu_multi* m, const char* bases, const uint64_t* read_offsets,
+                                                    uint64_t num_reads, uint64_t* kmer_ids, sshash_streaming_report* report);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,7 @@ SYMBOLS = {
     "sshash_gpu_close": (C.c_int, [C.c_void_p]),
     "sshash_gpu_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "sshash_gpu_lookup_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sshash_gpu_lookup_batch_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     "sshash_gpu_lookup_batch_ascii": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sshash_gpu_is_member_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     "sshash_gpu_minimizer_partition_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -66,6 +67,15 @@ SYMBOLS = {
     "sshash_gpu_streaming_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                              C.POINTER(StreamingReport), C.c_void_p]),
     "sshash_gpu_streaming_query_from_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(StreamingReport)]),
+    "sshash_gpu_multi_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sshash_gpu_multi_close": (C.c_int, [C.c_void_p]),
+    "sshash_gpu_multi_num_devices": (C.c_int, [C.c_void_p]),
+    "sshash_gpu_multi_dict": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "sshash_gpu_multi_lookup_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "sshash_gpu_multi_lookup_batch_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "sshash_gpu_multi_is_member_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "sshash_gpu_multi_streaming_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                   C.POINTER(StreamingReport)]),
 }
 
 _lib = None

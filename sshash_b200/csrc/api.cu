@@ -148,6 +148,16 @@ bool is_device_pointer(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// device memory that lives on `device` itself (or managed memory): kernels use it in place.  Memory
+// of ANOTHER GPU is treated like host memory by the batched pipeline: staged chunk by chunk with
+// copy-engine transfers (cudaMemcpyDefault: peer-to-peer over NVLink when peer access is enabled).
+bool is_local_device_pointer(const void* p, int device) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeManaged || (a.type == cudaMemoryTypeDevice && a.device == device);
+}
+
 }  // namespace
 
 int sshash_b200::set_last_error(int status, const std::string& msg) { return fail(status, msg); }
@@ -537,8 +547,11 @@ void configure_l2(sshash_gpu_dict* d) {
     // (evict_last, window over the whole slab with hitRatio = persisting / window) beats the cold policy
     // (13.5 vs 12.8 G lookups/s forward, 13.3 vs 10.7 negative), so cold pilots are opt-in only.
     bool cold = false;
-    if (const char* pc = std::getenv("SSHASH_GPU_PILOTS_COLD")) cold = pc[0] == '1';
-    d->ix.pilots_cold = cold ? 1 : 0;
+    d->ix.pilots_cold = 0;
+    if (const char* pc = std::getenv("SSHASH_GPU_PILOTS_COLD")) {       // 1: cold policy, 2: evict_last with 64-byte fills
+        cold = pc[0] == '1';
+        d->ix.pilots_cold = pc[0] == '1' ? 1 : pc[0] == '2' ? 2 : 0;
+    }
     const uint64_t span = cold ? std::max<uint64_t>(c.hot_prefix_bytes, 256) : c.hot_bytes;
     if (want && c.max_window_bytes && c.max_persist_bytes && span) {
         size_t cur = 0;
@@ -589,7 +602,7 @@ template <typename Launch>
 int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void* out, uint64_t out_elem, uint64_t n,
                 void* user_stream, Launch launch) {
     if (n == 0) return SSHASH_GPU_OK;
-    const bool in_dev = is_device_pointer(in), out_dev = is_device_pointer(out);
+    const bool in_dev = is_local_device_pointer(in, d->device), out_dev = is_local_device_pointer(out, d->device);
     if (in_dev && out_dev) {
         cudaStream_t s = static_cast<cudaStream_t>(user_stream);   // NULL = the legacy default stream
         CU(launch(in, out, n, s));
@@ -597,7 +610,8 @@ int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void
     }
     WorkspaceLease ws(d);
     // SSHASH_GPU_BATCH_CHUNK: bytes per pipeline chunk of the larger of the two element streams
-    const uint64_t chunk = std::max<uint64_t>(1, env_bytes("SSHASH_GPU_BATCH_CHUNK", 32ull << 20) / std::max(in_elem, out_elem));
+    static const uint64_t chunk_bytes = env_bytes("SSHASH_GPU_BATCH_CHUNK", 32ull << 20);   // read once
+    const uint64_t chunk = std::max<uint64_t>(1, chunk_bytes / std::max(in_elem, out_elem));
     int c = 0;
     for (uint64_t off = 0; off < n; off += chunk, ++c) {
         const uint64_t cn = std::min(chunk, n - off);
@@ -605,10 +619,10 @@ int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void
         CU(ensure_slot(s, in_dev ? 0 : chunk * in_elem, out_dev ? 0 : chunk * out_elem));
         const void* din = static_cast<const uint8_t*>(in) + off * in_elem;
         void* dout = static_cast<uint8_t*>(out) + off * out_elem;
-        if (!in_dev) { CU(cudaMemcpyAsync(s.d_in, din, cn * in_elem, cudaMemcpyHostToDevice, s.stream)); din = s.d_in; }
+        if (!in_dev) { CU(cudaMemcpyAsync(s.d_in, din, cn * in_elem, cudaMemcpyDefault, s.stream)); din = s.d_in; }
         void* kout = out_dev ? dout : s.d_out;
         CU(launch(din, kout, cn, s.stream));
-        if (!out_dev) CU(cudaMemcpyAsync(dout, s.d_out, cn * out_elem, cudaMemcpyDeviceToHost, s.stream));
+        if (!out_dev) CU(cudaMemcpyAsync(dout, s.d_out, cn * out_elem, cudaMemcpyDefault, s.stream));
     }
     for (auto& s : ws->slots) if (s.stream) CU(cudaStreamSynchronize(s.stream));
     return SSHASH_GPU_OK;
@@ -685,7 +699,8 @@ SSHASH_ENTRY(sshash_gpu_info, (const sshash_gpu_dict* dict, sshash_gpu_info_t* o
 // stream before handing it back (the direct kernel stays fully asynchronous).
 static bool use_binned(const sshash_gpu_dict* dict, const void* in, const void* out, uint64_t n) {
     const BinPlan& bp = dict->ctx.bins;
-    return bp.enabled && bp.n_bins && n >= bp.min_queries && is_device_pointer(in) && is_device_pointer(out);
+    return bp.enabled && bp.n_bins && n >= bp.min_queries && is_local_device_pointer(in, dict->device) &&
+           is_local_device_pointer(out, dict->device);
 }
 
 static int lookup_binned_device(const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, bool check_rc, uint64_t* ids,
@@ -747,6 +762,23 @@ static int lookup_common(const sshash_gpu_dict* dict, const void* queries, bool 
 SSHASH_ENTRY(sshash_gpu_lookup_batch, (const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
                             uint64_t* kmer_ids, sshash_lookup_result* full, void* stream), (dict, kmers, n, check_reverse_complement, kmer_ids, full, stream)) {
     return lookup_common(dict, kmers, false, n, check_reverse_complement, kmer_ids, full, stream);
+}
+
+SSHASH_ENTRY(sshash_gpu_lookup_batch_u32, (const sshash_gpu_dict* dict, const uint64_t* kmers, uint64_t n, int check_reverse_complement,
+                                        uint32_t* kmer_ids32, void* stream), (dict, kmers, n, check_reverse_complement, kmer_ids32, stream)) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (dict->ix.num_kmers >= 0xffffffffull) return fail(SSHASH_GPU_EINVAL, "32-bit ids need a dictionary with fewer than 2^32 - 1 k-mers");
+    if (n == 0) return SSHASH_GPU_OK;
+    if (!kmers || !kmer_ids32) return fail(SSHASH_GPU_EINVAL, "null argument");
+    const DeviceIndex& ix = dict->ix;
+    const LaunchCtx& sms = dict->ctx;
+    const bool rc = check_reverse_complement != 0;
+    if (use_binned(dict, kmers, kmer_ids32, n)) return lookup_binned_device(dict, kmers, n, rc, nullptr, kmer_ids32, nullptr, stream);
+    return run_batched(dict, kmers, 8ull * ix.kmer_words, kmer_ids32, 4, n, stream,
+                       [&](const void* in, void* out, uint64_t cn, cudaStream_t s) {
+                           return launch_lookup(ix, sms, in, false, cn, rc, nullptr, nullptr, nullptr, s, static_cast<uint32_t*>(out));
+                       });
 }
 
 SSHASH_ENTRY(sshash_gpu_lookup_batch_ascii, (const sshash_gpu_dict* dict, const char* kmers, uint64_t n, int check_reverse_complement,

@@ -155,11 +155,11 @@ __device__ __forceinline__ uint64_t low_mask(uint32_t bits) {  // bits in [0,64]
 // POLICY: 0 = COLD, 1 = HOT (the historical bool spelling still works: false / true), 2 = NORMAL: no hint, full
 // 128-byte fills -- used by the partition-major path for pilots and codewords, which it visits one
 // partition at a time so that they are L2 hits by schedule (binned.cu).
-constexpr int kCold = 0, kHot = 1, kNormal = 2;
+constexpr int kCold = 0, kHot = 1, kNormal = 2, kHot64 = 3;   // kHot64: evict_last with 64-byte fills
 template <int POLICY>
 __device__ __forceinline__ uint64_t l2_policy() {
     uint64_t p;
-    if (POLICY == kHot) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    if (POLICY == kHot || POLICY == kHot64) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     else asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
@@ -171,6 +171,7 @@ __device__ __forceinline__ uint64_t ld64(const uint64_t* __restrict__ p) {
     uint64_t v;
     if (POLICY == kHot) asm("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<kHot>()));
     else if (POLICY == kNormal) asm("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (POLICY == kHot64) asm("ld.global.nc.L2::cache_hint.L2::64B.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<kHot64>()));
     else asm("ld.global.nc.L2::cache_hint.L2::64B.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_policy<kCold>()));
     return v;
 }
@@ -478,8 +479,9 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
     const uint32_t bucket = mulhi_64x32(H, num_buckets);
     const uint64_t* pw = ix.pilots + pilots_word;
     const uint64_t pilot = BINNED ? compact_get<kNormal>(pw, pilot_width, low_mask(pilot_width), bucket)
-                           : ix.pilots_cold ? compact_get<kCold>(pw, pilot_width, low_mask(pilot_width), bucket)
-                                            : compact_get<kHot>(pw, pilot_width, low_mask(pilot_width), bucket);
+                           : ix.pilots_cold == 1 ? compact_get<kCold>(pw, pilot_width, low_mask(pilot_width), bucket)
+                           : ix.pilots_cold == 2 ? compact_get<kHot64>(pw, pilot_width, low_mask(pilot_width), bucket)
+                                                 : compact_get<kHot>(pw, pilot_width, low_mask(pilot_width), bucket);
     uint32_t pos = mulhi_64x32((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, table_size);
     if (pos >= num_keys) pos = ld32<true>(ix.free_slots + free_off + (pos - num_keys));
     return offset + pos;

@@ -61,7 +61,7 @@ __device__ __forceinline__ Kmer<2> pack_ascii<2>(const char* __restrict__ s, uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// batched dictionary::lookup.  MODE 0: ids, 1: ids + full records, 2: membership bytes
+// batched dictionary::lookup.  MODE 0: ids, 1: ids + full records, 2: membership bytes, 3: 32-bit ids (`ids` reinterpreted)
 //
 // One thread per query.  On a regular (non-canonical) index a k-mer stored in the other
 // orientation misses the forward pass and needs a second pass on its reverse complement
@@ -74,6 +74,7 @@ template <int MODE>
 __device__ __forceinline__ void emit(uint64_t i, const LookupResult& r, uint64_t* __restrict__ ids,
                                      sshash_lookup_result* __restrict__ full, uint8_t* __restrict__ member) {
     if (MODE == 2) member[i] = r.kmer_id != ~0ull;
+    else if (MODE == 3) __stcs(reinterpret_cast<uint32_t*>(ids) + i, (uint32_t)r.kmer_id);   // u32 ids: UINT32_MAX = not found
     else {
         if (ids) __stcs(ids + i, r.kmer_id);
         if (MODE == 1) store_full(full, i, r);
@@ -1068,8 +1069,19 @@ std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launch_count() { return g_launches.load(); }
 
 cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const void* queries, bool ascii, uint64_t n, bool check_rc,
-                          uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream) {
+                          uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream, uint32_t* ids32) {
     if (n == 0) return cudaSuccess;
+    if (ids32) {                                           // 32-bit ids: packed queries, ids only
+        if (ascii || ids || full || member) return cudaErrorInvalidValue;
+        const int g32 = grid_for(n, ctx.sm_count, 2 * (ix.canonical && ix.kmer_words == 2 ? kLookupMinBlocksWideCanon : kLookupMinBlocks));
+        uint64_t* out = reinterpret_cast<uint64_t*>(ids32);
+        const int rcf = check_rc ? 1 : 0;
+        if (ix.kmer_words == 1)
+            return ix.canonical ? launch(lookup_kernel<1, 3, false, true, kLookupMinBlocks>, g32, stream, ctx, ix, queries, n, rcf, out, full, member)
+                                : launch(lookup_kernel<1, 3, false, false, kLookupMinBlocks>, g32, stream, ctx, ix, queries, n, rcf, out, full, member);
+        return ix.canonical ? launch(lookup_kernel<2, 3, false, true, kLookupMinBlocksWideCanon>, g32, stream, ctx, ix, queries, n, rcf, out, full, member)
+                            : launch(lookup_kernel<2, 3, false, false, kLookupMinBlocks>, g32, stream, ctx, ix, queries, n, rcf, out, full, member);
+    }
     const int grid = grid_for(n, ctx.sm_count, 2 * (ix.canonical && ix.kmer_words == 2 ? kLookupMinBlocksWideCanon : kLookupMinBlocks));
     const int mode = member ? 2 : (full ? 1 : 0);
     const int crc = check_rc ? 1 : 0;

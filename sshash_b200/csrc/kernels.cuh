@@ -44,9 +44,10 @@ struct LaunchCtx {
 uint64_t kernel_launch_count();
 
 // Batched dictionary::lookup.  `queries`: packed k-mers (ascii = false) or n*k characters.
-// Exactly one of {ids and/or full, member} is produced; all pointers are DEVICE pointers.
+// Exactly one of {ids and/or full, member, ids32} is produced; all pointers are DEVICE pointers.
+// ids32: 32-bit ids (UINT32_MAX = not found) for dictionaries with fewer than 2^32 - 1 k-mers.
 cudaError_t launch_lookup(const DeviceIndex& ix, const LaunchCtx& ctx, const void* queries, bool ascii, uint64_t n, bool check_rc,
-                          uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream);
+                          uint64_t* ids, sshash_lookup_result* full, uint8_t* member, cudaStream_t stream, uint32_t* ids32 = nullptr);
 
 cudaError_t launch_access(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* ids, uint64_t n, uint64_t* kmers_out,
                           cudaStream_t stream);

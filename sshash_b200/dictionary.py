@@ -144,6 +144,21 @@ class Dictionary:
                                                 None, _stream_for(kmers, stream)))
         return ids
 
+    def lookup_batch_u32(self, kmers, check_reverse_complement: bool = True, out=None, stream: Optional[int] = None):
+        """lookup_batch with 32-bit ids (dictionaries with < 2^32 - 1 k-mers): "not found" is
+        UINT32_MAX (numpy uint32; torch: int32 bit patterns, i.e. -1)."""
+        kmers = self._prep_in(kmers)
+        n = self._count(kmers)
+        if out is None:
+            if _is_torch(kmers):
+                import torch
+                out = torch.empty(n, dtype=torch.int32, device=kmers.device)
+            else:
+                out = np.empty(n, dtype=np.uint32)
+        check(self._lib.sshash_gpu_lookup_batch_u32(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(out),
+                                                    _stream_for(kmers, stream)))
+        return out
+
     def lookup_batch_ascii(self, strings: bytes, check_reverse_complement: bool = True, full: bool = False):
         """Batched dictionary::lookup(char const*, bool): n*k characters, no validation."""
         buf = np.frombuffer(strings, dtype=np.uint8)
@@ -254,6 +269,113 @@ class Dictionary:
         rep = StreamingReport()
         check(self._lib.sshash_gpu_streaming_query_from_file(self._h, filename.encode(), int(multiline), C.byref(rep)))
         return rep.as_dict()
+
+
+class MultiDictionary:
+    """The same index replicated on several GPUs of one box behind ONE handle of the C ABI
+    (sshash_gpu_multi_*): batches are sharded by query across the GPUs inside the library, results
+    come back in query order.  numpy arrays = host buffers; a torch CUDA tensor on any GPU of the
+    box is used in place by its GPU and reached peer-to-peer by the others."""
+
+    def __init__(self, index_filename: str, devices=None, max_k: int = 0):
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        if devices is None:
+            arr, n = None, 0
+        else:
+            devices = list(devices)
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+        check(self._lib.sshash_gpu_multi_open(index_filename.encode(), arr, n, max_k, C.byref(self._h)))
+        self.num_devices = int(self._lib.sshash_gpu_multi_num_devices(self._h))
+        info = Info()
+        check(self._lib.sshash_gpu_info(self._lib.sshash_gpu_multi_dict(self._h, 0), C.byref(info)))
+        self.info = {n_: int(getattr(info, n_)) for n_, _ in Info._fields_}
+        self.words = 1 if self.info["max_k"] == 31 else 2
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sshash_gpu_multi_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def k(self) -> int: return self.info["k"]
+    def num_kmers(self) -> int: return self.info["num_kmers"]
+
+    def _n(self, kmers) -> int:
+        n = kmers.numel() if _is_torch(kmers) else kmers.size
+        if n % self.words:
+            raise ValueError("packed k-mer buffer length must be a multiple of %d words" % self.words)
+        return n // self.words
+
+    def _in(self, kmers):
+        if _is_torch(kmers):
+            return kmers if kmers.is_contiguous() else kmers.contiguous()
+        return np.ascontiguousarray(kmers, dtype=np.uint64)
+
+    def _out(self, ref, n, np_dtype):
+        if _is_torch(ref):
+            import torch
+            return torch.empty(n, dtype={np.uint64: torch.int64, np.uint32: torch.int32, np.uint8: torch.uint8}[np_dtype],
+                               device=ref.device)
+        return np.empty(n, dtype=np_dtype)
+
+    def _sync(self, kmers):
+        if _is_torch(kmers) and kmers.is_cuda:      # the library works on its own streams
+            import torch
+            torch.cuda.current_stream(kmers.device).synchronize()
+
+    def lookup_batch(self, kmers, check_reverse_complement: bool = True, out=None):
+        kmers = self._in(kmers)
+        n = self._n(kmers)
+        ids = out if out is not None else self._out(kmers, n, np.uint64)
+        self._sync(kmers)
+        check(self._lib.sshash_gpu_multi_lookup_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(ids)))
+        return ids
+
+    def lookup_batch_u32(self, kmers, check_reverse_complement: bool = True, out=None):
+        kmers = self._in(kmers)
+        n = self._n(kmers)
+        ids = out if out is not None else self._out(kmers, n, np.uint32)
+        self._sync(kmers)
+        check(self._lib.sshash_gpu_multi_lookup_batch_u32(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(ids)))
+        return ids
+
+    def is_member_batch(self, kmers, check_reverse_complement: bool = True):
+        kmers = self._in(kmers)
+        n = self._n(kmers)
+        out = self._out(kmers, n, np.uint8)
+        self._sync(kmers)
+        check(self._lib.sshash_gpu_multi_is_member_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(out)))
+        return out if _is_torch(out) else out.astype(bool)
+
+    def streaming_batch(self, bases, read_offsets, want_ids: bool = True):
+        if isinstance(bases, (bytes, bytearray)):
+            bases = np.frombuffer(bases, dtype=np.uint8)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_offsets = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+        nreads = read_offsets.size - 1
+        ids = None
+        if want_ids:
+            lens = np.diff(read_offsets.astype(np.int64))
+            ids = np.empty(max(int(np.maximum(lens - self.k() + 1, 0).sum()), 1), dtype=np.uint64)
+        rep = StreamingReport()
+        check(self._lib.sshash_gpu_multi_streaming_batch(self._h, _ptr(bases), _ptr(read_offsets), max(nreads, 0),
+                                                         _ptr(ids) if want_ids else None, C.byref(rep)))
+        if want_ids:
+            lens = np.diff(read_offsets.astype(np.int64))
+            ids = ids[: int(np.maximum(lens - self.k() + 1, 0).sum())]
+        return ids, rep.as_dict()
 
 
 def launch_count() -> int:

@@ -23,6 +23,7 @@ VARIANTS = {
     "r1_layout": {"SSHASH_GPU_LOCATE": "legacy", "SSHASH_GPU_BINNED": "0"},
     "direct": {"SSHASH_GPU_BINNED": "0"},
     "direct+pilots_cold": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "1"},
+    "direct+pilots_hot64": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "2"},
     "binned": {"SSHASH_GPU_BINNED": "1"},
     "binned_noprefetch": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_PREFETCH": "0"},
     "binned_lookahead2": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_LOOKAHEAD": "2"},
