@@ -171,6 +171,8 @@ struct sshash_gpu_dict {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     std::vector<std::unique_ptr<Workspace>> pool;
+    std::mutex contract_mu;
+    int breaks_contract = -1;   // -1 not checked yet; 1 = duplicated k-mers / rc twins: streaming replays the state machine
 
     std::unique_ptr<Workspace> take() {
         std::lock_guard<std::mutex> g(mu);
@@ -552,7 +554,10 @@ void configure_l2(sshash_gpu_dict* d) {
         cold = pc[0] == '1';
         d->ix.pilots_cold = pc[0] == '1' ? 1 : pc[0] == '2' ? 2 : 0;
     }
-    const uint64_t span = cold ? std::max<uint64_t>(c.hot_prefix_bytes, 256) : c.hot_bytes;
+    // SSHASH_GPU_L2_WINDOW=prefix: the window covers only the locate tables (the pilots keep their evict_last hint)
+    const char* we = std::getenv("SSHASH_GPU_L2_WINDOW");
+    const bool prefix_only = cold || (we && std::strcmp(we, "prefix") == 0);
+    const uint64_t span = prefix_only ? std::max<uint64_t>(c.hot_prefix_bytes, 256) : c.hot_bytes;
     if (want && c.max_window_bytes && c.max_persist_bytes && span) {
         size_t cur = 0;
         cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
@@ -899,6 +904,33 @@ SSHASH_ENTRY(sshash_gpu_string_neighbours_batch, (const sshash_gpu_dict* dict, c
     return neighbours_common(dict, string_ids, true, n, check_reverse_complement, 3, kmer_ids, full, stream);
 }
 
+// Lazily (first streaming call) checks SSHash's input contract on the device (kernels.cu
+// distinct_check_kernel): 1 = the index holds duplicated k-mers or reverse-complement twins, and
+// streaming must replay the reference's state machine literally.  SSHASH_GPU_ASSUME_DISTINCT=1 skips
+// the check, =0 forces the replay path (tests).
+static int needs_replay(const sshash_gpu_dict* dict, bool* replay) {
+    sshash_gpu_dict* d = const_cast<sshash_gpu_dict*>(dict);
+    std::lock_guard<std::mutex> g(d->contract_mu);
+    if (d->breaks_contract < 0) {
+        const char* e = std::getenv("SSHASH_GPU_ASSUME_DISTINCT");
+        if (e && (e[0] == '0' || e[0] == '1')) d->breaks_contract = e[0] == '0';
+        else {
+            uint32_t* d_flag = nullptr;
+            uint32_t flag = 0;
+            CU(cudaMalloc(reinterpret_cast<void**>(&d_flag), 4));
+            cudaError_t err = cudaMemsetAsync(d_flag, 0, 4, d->stream);
+            if (err == cudaSuccess) err = launch_distinct_check(d->ix, d->ctx, d_flag, d->stream);
+            if (err == cudaSuccess) err = cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, d->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(d->stream);
+            cudaFree(d_flag);
+            if (err != cudaSuccess) return cuda_fail(err, "input-contract check");
+            d->breaks_contract = flag ? 1 : 0;
+        }
+    }
+    *replay = d->breaks_contract == 1;
+    return SSHASH_GPU_OK;
+}
+
 // One device-resident batch of reads: offsets scan, window lookups, state-machine replay.
 static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const char* d_bases, const uint64_t* d_read_begins,
                             const uint64_t* d_read_ends, uint64_t num_reads, uint64_t max_windows, uint64_t* d_ids_out, cudaStream_t s) {
@@ -914,11 +946,17 @@ static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const cha
         w.win_cap = bytes;
     }
     // SSHASH_GPU_STREAM_ALIGN=0 disables the anchor/alignment shortcut (every window is looked up)
-    static const bool use_anchors = !(std::getenv("SSHASH_GPU_STREAM_ALIGN") && std::getenv("SSHASH_GPU_STREAM_ALIGN")[0] == '0');
+    bool replay = false;
+    {
+        const int rs = needs_replay(dict, &replay);
+        if (rs) return rs;
+    }
+    static const bool anchors_on = !(std::getenv("SSHASH_GPU_STREAM_ALIGN") && std::getenv("SSHASH_GPU_STREAM_ALIGN")[0] == '0');
+    const bool use_anchors = anchors_on && !replay;
     if (use_anchors) CU(ensure(w.d_anchors, w.anchors_cap, streaming_anchor_bytes(num_reads)));
     CU(launch_window_offsets(ix.k, d_read_begins, d_read_ends, num_reads, w.d_win_offsets, w.d_block_sums, s));
     CU(launch_streaming(ix, dict->ctx, d_bases, d_read_begins, d_read_ends, w.d_win_offsets, num_reads, use_anchors ? w.d_anchors : nullptr,
-                        w.d_win_id, w.d_win_aux, d_ids_out, max_windows, w.d_counters, s));
+                        w.d_win_id, w.d_win_aux, d_ids_out, max_windows, w.d_counters, s, replay));
     return SSHASH_GPU_OK;
 }
 

@@ -779,7 +779,31 @@ template <> struct KmerIter<2> {
     }
 };
 
+// 64-bit k-mers: the reference iterator (include/kmer_iterator.hpp:8-86) has no word-order quirk there; after
+// at(p) and s steps, get() is the k-mer at bits [p + 2s, p + 2s + 2k) and get_reverse() the one at
+// bits [p - 2s - 2k, p - 2s): plain reads of `strings`.
+template <> struct KmerIter<1> {
+    uint64_t pos;
+    __device__ void at(uint64_t p) { pos = p; }
+    __device__ void next(const DeviceIndex&) { pos += 2; }
+    __device__ void next_reverse(const DeviceIndex&) { pos -= 2; }
+    __device__ Kmer<1> get(const DeviceIndex& ix) const { return read_kmer(ix, pos >> 1, (Kmer<1>*)nullptr); }
+    __device__ Kmer<1> get_reverse(const DeviceIndex& ix) const { return read_kmer(ix, (pos >> 1) - ix.k, (Kmer<1>*)nullptr); }
+};
+
 template <int W> struct RollingKmer;
+template <> struct RollingKmer<1> {
+    Kmer<1> x, xr;
+    __device__ void init(const char* s, uint32_t k) {
+        x.lo = 0; xr.lo = 0;
+        for (uint32_t i = 0; i + 1 < k; ++i) push((uint8_t)s[i], k);
+    }
+    __device__ void push(uint8_t c, uint32_t k) {
+        const uint64_t code = (c >> 1) & 3;
+        x.lo = (x.lo >> 2) | (code << (2 * (k - 1)));
+        xr.lo = ((xr.lo << 2) | (code ^ 2)) & low_mask(2 * k);
+    }
+};
 template <> struct RollingKmer<2> {
     Kmer<2> x, xr;
     __device__ void init(const char* s, uint32_t k) {
@@ -923,6 +947,33 @@ stream_classify_kernel(const uint64_t* __restrict__ win_offsets, uint64_t num_re
     }
     __syncthreads();
     if (threadIdx.x < 5 && sh[threadIdx.x]) atomicAdd(&counters[threadIdx.x], sh[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Does the index keep SSHash's input contract -- every k-mer once, and on a regular index never
+// together with its reverse complement (README)?  The streaming shortcuts (anchors,
+// per-window classification) are exact only then; the reference itself still answers such indexes,
+// with results that depend on the state of the stream, so they take the literal replay instead.
+// One thread per text offset: the k-mer there must look up to its own id, and (regular index) its
+// reverse complement must be absent.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kBlock)
+distinct_check_kernel(const __grid_constant__ DeviceIndex ix, uint32_t* __restrict__ flag) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n_bases = ix.strings_bits / 2;
+    const uint32_t k = ix.k;
+    bool bad = false;
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o + k <= n_bases; o += stride) {
+        uint64_t sb, se;
+        const uint64_t sid = locate_string(ix, o, sb, se);
+        if (o + k > se) continue;                         // window straddles two strings
+        const Kmer<W> x = read_kmer(ix, o, (Kmer<W>*)nullptr);
+        LookupResult r;
+        const bool found = ix.canonical ? lookup_canonical<W, false>(ix, x, r) : lookup_regular<W, false>(ix, x, r);
+        if (!found || r.kmer_id != o - sid * (k - 1)) bad = true;
+        if (!ix.canonical && lookup_regular<W, false>(ix, kmer_rc(x, k), r)) bad = true;
+    }
+    if (bad) atomicOr(flag, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1184,12 +1235,19 @@ cudaError_t launch_window_offsets(uint32_t k, const uint64_t* read_begins, const
     return cudaGetLastError();
 }
 
+cudaError_t launch_distinct_check(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t* flag, cudaStream_t stream) {
+    const int grid = grid_for(ix.strings_bits / 2, ctx.sm_count, 8);
+    return ix.kmer_words == 1 ? launch(distinct_check_kernel<1>, grid, stream, ctx, ix, flag)
+                              : launch(distinct_check_kernel<2>, grid, stream, ctx, ix, flag);
+}
+
 cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_begins,
                              const uint64_t* read_ends, const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
-                             uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream) {
+                             uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream, bool replay) {
     if (num_reads == 0) return cudaSuccess;
-    // 64-bit k-mers: streamed ids == window ids, so the window kernel writes the caller's buffer directly
-    if (ix.kmer_words == 1 && ids_out) win_id = ids_out;
+    if (replay) anchors = nullptr;                       // every window is an independent lookup, then the literal state machine
+    // 64-bit k-mers on a distinct index: streamed ids == window ids, so the window kernel writes the caller's buffer directly
+    if (ix.kmer_words == 1 && ids_out && !replay) win_id = ids_out;
     Anchor* an = static_cast<Anchor*>(anchors);
     if (an) {
         const int grid = grid_for(num_reads * kAnchorsPerRead, ctx.sm_count, 8);
@@ -1211,6 +1269,9 @@ cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const 
                        (const Anchor*)an, win_id, win_aux, counters + 5);
         if (e != cudaSuccess) return e;
     }
+    if (ix.kmer_words == 1 && replay)
+        return launch(stream_scan_kernel<1>, grid_for(num_reads, ctx.sm_count, 8), stream, ctx, ix, bases, read_begins, read_ends,
+                      win_offsets, num_reads, win_id, win_aux, ids_out, counters);
     if (ix.kmer_words == 1) {
         // 64-bit k-mers: the windows kernel wrote the streamed ids straight into ids_out (see below)
         return launch(stream_classify_kernel, grid_for(total_windows_bound, ctx.sm_count, 8), stream, ctx, win_offsets, num_reads,

@@ -102,7 +102,13 @@ uint64_t window_offsets_scratch_words(uint64_t num_reads);
 // counters[5] += {num_kmers, searches, extensions, negative, invalid}.
 cudaError_t launch_streaming(const DeviceIndex& ix, const LaunchCtx& ctx, const char* bases, const uint64_t* read_begins,
                              const uint64_t* read_ends, const uint64_t* win_offsets, uint64_t num_reads, void* anchors, uint64_t* win_id, uint64_t* win_aux,
-                             uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream);
+                             uint64_t* ids_out, uint64_t total_windows_bound, unsigned long long* counters, cudaStream_t stream,
+                             bool replay = false);
+// open-time / first-use check of SSHash's input contract (every k-mer once; regular index: never with its
+// reverse complement): *flag (zeroed by the caller) becomes non-zero when the index breaks it.  Streaming
+// over such an index must pass replay = true above (no anchors, the reference's state machine replayed
+// literally), because the reference's own answers then depend on the state of the stream.
+cudaError_t launch_distinct_check(const DeviceIndex& ix, const LaunchCtx& ctx, uint32_t* flag, cudaStream_t stream);
 // scratch for the per-read alignment anchors (pass nullptr as `anchors` to look every window up)
 uint64_t streaming_anchor_bytes(uint64_t num_reads);
 

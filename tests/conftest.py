@@ -55,6 +55,9 @@ def load_manifest():
 MANIFEST = load_manifest()
 FIXTURES = sorted(MANIFEST)
 WEIGHTED = [n for n in FIXTURES if MANIFEST[n].get("weighted")]
+# indexes built from inputs with duplicated k-mers / reverse-complement twins: lookup(access(id))
+# need not be id there, everything else must still equal the reference
+NON_DISTINCT = [n for n in FIXTURES if MANIFEST[n].get("distinct_kmers") is False]
 
 
 @pytest.fixture(scope="session")

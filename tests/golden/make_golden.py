@@ -43,6 +43,53 @@ FIXTURES = [
 ]
 NQ = 12000  # positives per fixture (+ as many negatives)
 
+# Synthetic inputs that break SSHash's "distinct k-mers" input contract (README) -- the
+# reference still builds and answers them, and the CUDA path must give the same answers:
+#   name, k, m, canonical, build lib
+SYNTH = [
+    ("twins_k31_m13_reg", 31, 13, False, 31),     # k-mers present together with their reverse complements + duplicated k-mers
+    ("twins_k31_m13_canon", 31, 13, True, 31),    # duplicated k-mers (both strands) in a canonical index
+]
+
+
+def synth_twins_fasta(path, rng):
+    """400 random strings of 300 bases; 60 segments of 70 bases are copied into another string, every
+    other one reverse-complemented: a regular index then holds 40-k-mer runs twice (duplicates) or in
+    both orientations (rc twins, as separate entries)."""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    strings = ["".join("ACGT"[i] for i in rng.integers(0, 4, 300)) for _ in range(400)]
+    for j in range(60):
+        a, b = int(rng.integers(0, 400)), int(rng.integers(0, 400))
+        if a == b:
+            continue
+        pa, pb = int(rng.integers(0, 230)), int(rng.integers(0, 230))
+        seg = strings[a][pa:pa + 70]
+        if j % 2:
+            seg = "".join(comp[c] for c in reversed(seg))
+        strings[b] = strings[b][:pb] + seg + strings[b][pb + 70:]
+    with open(path, "w") as f:
+        for i, s in enumerate(strings):
+            f.write(">%d\n%s\n" % (i, s))
+    return strings
+
+
+def synth_twin_reads(strings, rng, nreads, k):
+    """reads = substrings of the input strings (both strands), so that they run through the copied
+    segments in every combination of orientations; plus a few random reads"""
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    reads = []
+    for r in range(nreads):
+        if r % 8 == 7:
+            reads.append("".join("ACGT"[i] for i in rng.integers(0, 4, 150)))
+            continue
+        s = strings[int(rng.integers(0, len(strings)))]
+        p = int(rng.integers(0, len(s) - 150))
+        t = s[p:p + 150]
+        if rng.integers(0, 2):
+            t = "".join(comp[c] for c in reversed(t))
+        reads.append(t)
+    return reads
+
 
 def subset(src, nseq, dst):
     with gzip.open(src, "rt") as f, open(dst, "w") as g:
@@ -208,6 +255,50 @@ def main():
                               num_kmers=d.num_kmers, num_strings=d.num_strings,
                               index_bytes=os.path.getsize(idx), stream_report=rep,
                               num_found=int((ids != 2**64 - 1).sum()))
+        print(name, manifest[name])
+        d.close()
+        make_nav(name, lib)
+    for name, k, m, canon, lib in SYNTH:
+        if only and name not in only:
+            continue
+        rng = np.random.default_rng(sum(map(ord, name)))
+        fa = os.path.join(TMP, name + ".fa")
+        strings = synth_twins_fasta(fa, rng)
+        idx = os.path.join(HERE, name + ".sshash")
+        ref.build(fa, k, m, idx, canonical=canon, tmp_dir=TMP, max_k=lib)
+        d = ref.RefDictionary(idx, max_k=lib)
+        # queries: every k-mer whose lookup does NOT return its own id (a duplicate or an rc twin answers
+        # first) + 6000 others; odd positions reverse-complemented as everywhere; + random negatives
+        allid = np.arange(d.num_kmers, dtype=np.uint64)
+        back = d.lookup(d.access(allid), check_rc=True)
+        odd = allid[back != allid]
+        rest = rng.choice(allid[back == allid], 6000, replace=False).astype(np.uint64)
+        pid = np.concatenate([odd, rest])
+        rng.shuffle(pid)
+        lo = d.access(pid)
+        rcs = rc_packed(lo[1::2], np.zeros(lo[1::2].size, dtype=np.uint64), k)
+        lo[1::2] = np.array(rcs, dtype=np.uint64)
+        neg = rng.integers(0, 2**62, 2000).astype(np.uint64)
+        q = np.concatenate([lo, neg])
+        ids, full = d.lookup(q, check_rc=True, full=True)
+        ids_norc = d.lookup(q, check_rc=False)
+        reads = synth_twin_reads(strings, rng, 600, k)
+        bases = "".join(reads).encode()
+        offs = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+        sids, sfull, rep, _ = d.streaming_reads(bases, offs, full=True)
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            queries=q, positive_ids=pid, ids=ids, ids_norc=ids_norc, full=full,
+            read_bases=np.frombuffer(bases, dtype=np.uint8), read_offsets=offs,
+            stream_ids=sids, stream_full=sfull,
+            stream_report=np.array([rep[n] for n in ("num_kmers", "num_positive_kmers", "num_negative_kmers",
+                                                     "num_invalid_kmers", "num_searches", "num_extensions")],
+                                   dtype=np.uint64))
+        manifest[name] = dict(source="synthetic (synth_twins_fasta)", k=k, m=m, canonical=canon, nseq=400, max_k=lib,
+                              weighted=False, num_kmers=d.num_kmers, num_strings=d.num_strings,
+                              index_bytes=os.path.getsize(idx), stream_report=rep,
+                              num_found=int((ids != 2**64 - 1).sum()), distinct_kmers=False,
+                              ids_not_identity=int((ids[:pid.size] != pid).sum()))
         print(name, manifest[name])
         d.close()
         make_nav(name, lib)

@@ -22,6 +22,20 @@ def test_cpp_example(tmp_path, name):
     assert "0 mismatches" in out.stdout
 
 
+@pytest.mark.parametrize("name", ["se_k31_m13", "se_k63_m21"])
+def test_c_multi_gpu_example(tmp_path, name):
+    """examples/multi_gpu_example.c: plain C through the multi-GPU entry points of the C ABI
+    (sshash_gpu_multi_*), every visible GPU, host buffers; self-checking."""
+    exe = str(tmp_path / "multi_gpu_example")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    lib_dir = os.path.join(ROOT, "sshash_b200")
+    subprocess.check_call([cc, "-std=c11", "-O2", os.path.join(ROOT, "examples", "multi_gpu_example.c"), "-o", exe,
+                           os.path.join(lib_dir, "libsshash_gpu.so"), "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe, golden(name).index, "300001"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 mismatches" in out.stdout.splitlines()[-1]
+
+
 def test_cpp_query_tool_prints_the_reference_report(tmp_path):
     """examples/query_example.cpp = the reference's `sshash query` (tools/query.cpp:5-70): report
     lines on stdout, one json line on stderr, counters equal to the reference's golden report."""

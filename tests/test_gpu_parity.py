@@ -109,7 +109,12 @@ def test_access_and_roundtrip(dicts, name):
     ids[:4] = [0, 1, d.num_kmers() - 1, d.num_kmers() - 2]
     kmers = d.access_batch(ids)
     got = d.lookup_batch(kmers.reshape(-1))
-    assert (got == ids).all()
+    if g.meta.get("distinct_kmers", True):
+        assert (got == ids).all()
+    else:   # duplicated k-mers / rc twins: the first occurrence in bucket order answers; it holds the same k-mer
+        assert (d.access_batch(got) == kmers).reshape(len(ids), -1).all(axis=1).sum() >= 0.4 * len(ids)
+        from oracle import port
+        assert (got == port.OracleDictionary(g.index, g.max_k).lookup(kmers.reshape(-1))).all()
     # access agrees with the reference on the golden positives (even positions are forward)
     acc = d.access_batch(g.z["positive_ids"]).reshape(npos, -1)
     assert (acc[0::2].reshape(-1) == g.z["queries"].reshape(-1, g.words)[:npos][0::2].reshape(-1)).all()
@@ -532,6 +537,91 @@ def test_binned_path_multi_partition_multi_range(tmp_path):
         assert (got[:m] == o.lookup(q[:m])).all()
         direct.close()
         binned.close()
+
+
+@pytest.mark.parametrize("name", ["se_k31_m13", "sal100_k31_m7_canon", "se_k63_m21", "sal100_k31_m7_reg"])
+def test_u32_ids(dicts, name):
+    """sshash_gpu_lookup_batch_u32: the low 32 bits of the reference ids, UINT32_MAX for "not found";
+    host buffers, device buffers, and the partition-major path."""
+    import torch
+    if name not in FIXTURES:
+        pytest.skip("fixture not present")
+    g, d = golden(name), dicts(name)
+    want = g.z["ids"].astype(np.uint32)          # INVALID truncates to UINT32_MAX
+    assert (d.lookup_batch_u32(g.z["queries"]) == want).all()
+    q = torch.from_numpy(g.z["queries"].view(np.int64)).cuda()
+    assert (d.lookup_batch_u32(q).cpu().numpy().view(np.uint32) == want).all()
+    b = _open_with_env(g.index, BINNED_ON, device=0, max_k=g.max_k)
+    assert (b.lookup_batch_u32(q).cpu().numpy().view(np.uint32) == want).all()
+    assert (b.lookup_batch_u32(q, check_reverse_complement=False).cpu().numpy().view(np.uint32) == g.z["ids_norc"].astype(np.uint32)).all()
+    b.close()
+
+
+@pytest.mark.parametrize("name", ["se_k31_m13", "se_k63_m21"])
+def test_multi_gpu_handle_matches_goldens(name):
+    """MultiDictionary = sshash_gpu_multi_* (every visible GPU, also a single one): host buffers,
+    device buffers on the first and on the last GPU, u32 ids, membership, streaming."""
+    import torch
+    import sshash_b200
+    g = golden(name)
+    m = sshash_b200.MultiDictionary(g.index, max_k=g.max_k)
+    assert m.num_devices == torch.cuda.device_count()
+    q, want = g.z["queries"], g.z["ids"]
+    assert (m.lookup_batch(q) == want).all()
+    assert (m.lookup_batch(q, check_reverse_complement=False) == g.z["ids_norc"]).all()
+    assert (m.lookup_batch_u32(q) == want.astype(np.uint32)).all()
+    assert (m.is_member_batch(q) == (want != INVALID)).all()
+    for dev in {0, m.num_devices - 1}:
+        qd = torch.from_numpy(q.view(np.int64)).to("cuda:%d" % dev)
+        ids = m.lookup_batch(qd)
+        assert ids.device == qd.device and (ids.cpu().numpy().view(np.uint64) == want).all()
+        assert (m.lookup_batch_u32(qd).cpu().numpy().view(np.uint32) == want.astype(np.uint32)).all()
+    sids, rep = m.streaming_batch(g.z["read_bases"], g.z["read_offsets"])
+    assert (sids == g.z["stream_ids"]).all()
+    assert rep == dict(zip(REPORT_KEYS, g.z["stream_report"].tolist()))
+    # ragged: fewer queries than GPUs, empty batch
+    assert (m.lookup_batch(q[: g.words]) == want[:1]).all()
+    assert m.lookup_batch(q[:0]).size == 0
+    m.close()
+
+
+def test_concurrent_batches_on_one_handle(dicts):
+    """include/sshash_gpu.h: the handle is immutable after open, any number of host threads may issue
+    batches concurrently.  Four threads, mixed host / device / full-record / streaming calls."""
+    import threading
+    import torch
+    g, d = golden("se_k31_m13"), dicts("se_k31_m13")
+    q, want = g.z["queries"], g.z["ids"]
+    errors = []
+
+    def worker(t):
+        try:
+            stream = torch.cuda.Stream()
+            for it in range(12):
+                kind = (t + it) % 4
+                if kind == 0:
+                    assert (d.lookup_batch(q) == want).all()
+                elif kind == 1:
+                    with torch.cuda.stream(stream):
+                        qd = torch.from_numpy(q.view(np.int64)).cuda()
+                        ids = d.lookup_batch(qd)
+                        stream.synchronize()
+                    assert (ids.cpu().numpy().view(np.uint64) == want).all()
+                elif kind == 2:
+                    full = d.lookup_batch(q[:6000], full=True)
+                    for f in full.dtype.names:
+                        assert (full[f] == g.z["full"][f][:6000]).all(), f
+                else:
+                    sids, rep = d.streaming_batch(g.z["read_bases"], g.z["read_offsets"])
+                    assert (sids == g.z["stream_ids"]).all()
+                    assert rep == dict(zip(REPORT_KEYS, g.z["stream_report"].tolist()))
+        except BaseException as e:   # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
 
 
 def test_sharded_lookup_with_peer_store_gather_two_gpus():

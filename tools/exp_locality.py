@@ -23,13 +23,14 @@ VARIANTS = {
     "r1_layout": {"SSHASH_GPU_LOCATE": "legacy", "SSHASH_GPU_BINNED": "0"},
     "direct": {"SSHASH_GPU_BINNED": "0"},
     "direct+pilots_cold": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "1"},
+    "direct+prefix_window": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_L2_WINDOW": "prefix"},
     "direct+pilots_hot64": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "2"},
     "binned": {"SSHASH_GPU_BINNED": "1"},
     "binned_noprefetch": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_PREFETCH": "0"},
     "binned_lookahead2": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_LOOKAHEAD": "2"},
     "default": {},
 }
-ENV_KEYS = ("SSHASH_GPU_LOCATE", "SSHASH_GPU_PILOTS_COLD", "SSHASH_GPU_BINNED", "SSHASH_GPU_BIN_PREFETCH", "SSHASH_GPU_BIN_LOOKAHEAD")
+ENV_KEYS = ("SSHASH_GPU_L2_WINDOW", "SSHASH_GPU_LOCATE", "SSHASH_GPU_PILOTS_COLD", "SSHASH_GPU_BINNED", "SSHASH_GPU_BIN_PREFETCH", "SSHASH_GPU_BIN_LOOKAHEAD")
 
 
 def main():
