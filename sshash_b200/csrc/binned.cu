@@ -12,23 +12,28 @@
 // random 64-byte DRAM fetch each.  What stays random is the one access the index layout cannot
 // coalesce: the k-mer comparison in `strings`, whose offset is unrelated to the MPHF position.
 //
-// Pipeline (all kernels asynchronous on one stream, no host round trip; exact, no overflow paths):
+// Pipeline (all kernels asynchronous on one stream, no host round trip; exact, no overflow paths; every
+// global store of the reordering steps leaves shared memory as full, coalesced sectors -- scattered
+// 8-byte stores were measured at 3.6x write amplification plus read-for-fill on B200's L2,
+// profiles/r2_human_binned_v2_scatter_unpermute_ncu_full.txt):
 //   A1  bin_count_kernel    minimizer + CityHash + partition per query -> meta1[i] = bin | pos,
 //                           histogram counts[range][bin] (range = 2^20 consecutive query indices)
 //   A2  bin_scan_kernel     exclusive scan in (bin, range) order -> every (range, bin) sub-run's slot
-//   A3  bin_scatter_kernel  records {k-mer, idx | pos | bin} written bin-major: a tile of 8192 records is
-//                           sorted by bin in shared memory and leaves as coalesced runs (one global atomic
-//                           per (tile, bin))
-//   B   lookup_binned_kernel  warps claim 128 consecutive records; each record is ONE pass of the
-//                           reference's lookup with the minimizer given (device_index.cuh); result ids
-//                           stored in record order; on a regular index misses are counted per sub-run
-//   C   unpermute_kernel    CTAs claim 2048-record chunks of the (range, bin) sub-runs in RANGE-major order,
-//                           so the whole grid works inside one or two ranges at a time: hits are stored to
-//                           ids[idx] (an 8 MB window of ids per range: the scattered stores merge in L2);
-//                           misses of a regular index with check_reverse_complement are appended,
-//                           reverse-complemented, to the round-2 list (src/dictionary.cpp:71-76) together
-//                           with their round-2 bin (A1 of round 2 is fused in here)
-//   round 2 = A2..C over the miss list; what still misses is stored as "not found".
+//   A3  bin_scatter_kernel  one CTA per TILE of 4096 consecutive queries: the tile's records {k-mer, idx |
+//                           pos | bin} are sorted by bin in shared memory and leave as coalesced runs
+//                           (one global reservation per (tile, bin)); the run of every (tile, bin) is
+//                           recorded in a table so that the tile's results can be found again
+//   B   lookup_binned_kernel  warps claim 128 consecutive records of the bin-major arrays; each record
+//                           is ONE pass of the reference's lookup with the minimizer given
+//                           (device_index.cuh); result ids stored in record order
+//   C1  gather_tile_kernel  one CTA per tile: the tile's results are collected from its <= n_bins runs
+//                           into a shared-memory image of ids[4096 t .. 4096 t + 4096) and stored as
+//                           one coalesced block; misses of a regular index with check_reverse_complement
+//                           are appended, reverse-complemented, to the round-2 list (src/dictionary.cpp:71-76)
+//                           together with their round-2 bin (A1 of round 2 is fused in here)
+//   round 2 = A2, A3, B over each tile's misses, then
+//   C2  patch_tile_kernel   one CTA per tile: the ids block is read back, patched with the round-2
+//                           results and stored again; what still misses stays "not found".
 // Canonical indexes take one round (src/dictionary.cpp:24-42); the minimizer tie case runs its
 // second attempt inline.
 #include <algorithm>
@@ -42,63 +47,48 @@ namespace {
 
 constexpr int kTile = 2048;                    // records per counting tile (kBlock threads x 8)
 constexpr int kTileItems = kTile / kBlock;
-constexpr int kSortTile = 8192;                // records per scatter tile (sorted in shared memory)
-constexpr int kSortThreads = 1024;
-constexpr int kSortItems = kSortTile / kSortThreads;
-constexpr int kChunk = 2048;                   // records per un-permute chunk
-constexpr int kChunkItems = kChunk / kBlock;
-constexpr uint32_t kRangeShift = 20;           // 2^20 query indices per output range (8 MB of u64 ids)
-constexpr uint32_t kPadIdx = 0xffffffffu;      // round-2 list: padding slot (ranges start on scatter-tile boundaries)
+constexpr int kOutTile = 4096;                 // queries per scatter / gather tile (32 KB of u64 ids)
+constexpr int kSortThreads = 512;
+constexpr int kSortItems = kOutTile / kSortThreads;
+constexpr uint32_t kRangeShift = 20;           // 2^20 query indices per range of the (range, bin) histogram
 constexpr int kClaimItems = 4;                 // records per lane and claim in phase B
 constexpr uint32_t kClaim = 32 * kClaimItems;
+constexpr uint32_t kMaxBins = 1024;
 
 // meta1 (u32): bin [0,16) | minimizer pos [16,22) | strand (canonical: minimizer taken from the rc) 22 | tie 23
 // record meta (u64): idx [0,32) | (meta1 >> 16) [32,40) | bin [40,56)
 
 struct Control {                 // device-resident control block of one round (u32 unless noted); s = range * n_bins + bin
     uint32_t* counts;            // [s]   records per sub-run
-    uint32_t* base;              // [s]   first slot of the sub-run in the bin-major record arrays
-    uint32_t* cursor;            // [s]   scatter cursor (starts at base)
-    uint32_t* chunk_start;       // [s+1] first un-permute chunk of the sub-run (range-major order)
-    uint32_t* miss_counts;       // [s]   misses per sub-run (round 1 of a regular index)
-    uint32_t* mcursor;           // [s]   next free slot of the sub-run's misses in the round-2 list
+    uint32_t* cursor;            // [s]   scatter cursor: first free slot of the sub-run in the bin-major record arrays
     uint32_t* bin_start;         // [n_bins + 1]
-    uint64_t* mstart;            // [n_ranges + 1] first slot of every range in the round-2 list; [n_ranges] = its length
-    unsigned long long* claims;  // [0] phase B record cursor, [1] phase C chunk cursor
+    unsigned long long* claims;  // [0] phase B record cursor, [1] length of the round-2 list so far
 };
 
-__device__ __forceinline__ uint32_t range_of_tile(uint64_t first_record, const uint64_t* __restrict__ mstart, uint32_t n_ranges) {
-    if (!mstart) return (uint32_t)(first_record >> kRangeShift);
-    uint32_t lo = 0, hi = n_ranges;                    // largest r with mstart[r] <= first_record (empty ranges share a start)
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) / 2;
-        if (mstart[mid] <= first_record) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-// exclusive scan of one value per thread over a CTA of NT threads (NT a multiple of 32, <= 1024)
+// exclusive scan of one value per thread over a CTA of NT threads (NT a multiple of 32, <= 1024);
+// scratch[NT / 32] holds the grand total afterwards
 template <int NT>
-__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /* NT / 32 + 1 */) {
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* scratch /* NT / 32 + 1 */) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += t; }
-    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();                                   // the previous use of scratch is over
+    if (lane == 31) scratch[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = lane < NT / 32 ? warp_sums[lane] : 0;
+        uint32_t w = lane < NT / 32 ? scratch[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (uint32_t)o) w += t; }
-        if (lane < NT / 32) warp_sums[lane] = w;        // inclusive
-        if (lane == 31) warp_sums[NT / 32] = w;         // grand total (lanes >= NT/32 added zeros)
+        if (lane < NT / 32) scratch[lane] = w;          // inclusive
+        if (lane == 31) scratch[NT / 32] = w;           // grand total (lanes >= NT/32 added zeros)
     }
     __syncthreads();
-    const uint32_t before = wid ? warp_sums[wid - 1] : 0;
+    const uint32_t before = wid ? scratch[wid - 1] : 0;
     return before + inc - v;
 }
 
-// bin | pos | flags of one query k-mer (A1; also run by C for the round-2 list)
+// bin | pos | flags of one query k-mer (A1; also run by C1 for the round-2 list)
 template <int W, bool CANON>
 __device__ __forceinline__ uint32_t bin_meta_of(const DeviceIndex& ix, Kmer<W> x, uint32_t bin_shift) {
     Minimizer mi = compute_minimizer(ix, x);
@@ -138,38 +128,24 @@ bin_count_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restr
     }
 }
 
-// ---- A2 (one CTA of kSortThreads) -------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads)
+// ---- A2 (one CTA of kMaxBins threads) ----------------------------------------------------------------
+__global__ void __launch_bounds__(kMaxBins)
 bin_scan_kernel(Control c, uint32_t n_ranges, uint32_t n_bins) {
-    extern __shared__ uint32_t sh[];                   // totals[n_bins + 1] + scan scratch [kSortThreads / 32 + 1]
-    uint32_t* totals = sh;
-    uint32_t* scratch = sh + n_bins + 1;
-    // per-bin totals, then their exclusive scan (n_bins <= kSortThreads)
-    uint32_t mine = 0;
+    __shared__ uint32_t scratch[kMaxBins / 32 + 1];
+    uint32_t mine = 0;                                 // this thread's bin: its total over the ranges
     if (threadIdx.x < n_bins)
         for (uint32_t r = 0; r < n_ranges; ++r) mine += c.counts[(uint64_t)r * n_bins + threadIdx.x];
-    const uint32_t ex = cta_exclusive_scan<kSortThreads>(mine, scratch);
-    if (threadIdx.x < n_bins) totals[threadIdx.x] = ex;
-    if (threadIdx.x == 0) totals[n_bins] = scratch[kSortThreads / 32];
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b <= n_bins; b += kSortThreads) c.bin_start[b] = totals[b];
+    const uint32_t ex = cta_exclusive_scan<kMaxBins>(mine, scratch);
     if (threadIdx.x < n_bins) {
-        uint32_t run = totals[threadIdx.x];
+        c.bin_start[threadIdx.x] = ex;
+        uint32_t run = ex;
         for (uint32_t r = 0; r < n_ranges; ++r) {
             const uint64_t s = (uint64_t)r * n_bins + threadIdx.x;
-            c.base[s] = run; c.cursor[s] = run;
+            c.cursor[s] = run;
             run += c.counts[s];
         }
     }
-    __syncthreads();
-    // chunk_start: exclusive scan of ceil(counts / kChunk) over the sub-runs in range-major order
-    const uint64_t runs = (uint64_t)n_ranges * n_bins;
-    const uint64_t per = (runs + kSortThreads - 1) / kSortThreads, s0 = per * threadIdx.x, s1 = s0 + per < runs ? s0 + per : runs;
-    uint32_t local = 0;
-    for (uint64_t s = s0; s < s1; ++s) local += (c.counts[s] + kChunk - 1) / kChunk;
-    uint32_t run = cta_exclusive_scan<kSortThreads>(local, scratch);
-    for (uint64_t s = s0; s < s1; ++s) { c.chunk_start[s] = run; run += (c.counts[s] + kChunk - 1) / kChunk; }
-    if (threadIdx.x == kSortThreads - 1) c.chunk_start[runs] = scratch[kSortThreads / 32];
+    if (threadIdx.x == 0) c.bin_start[n_bins] = scratch[kMaxBins / 32];
 }
 
 // ---- A3 -------------------------------------------------------------------------------------------
@@ -183,55 +159,63 @@ __device__ __forceinline__ Kmer<2> load_plain(const uint64_t* in, uint64_t i, Km
     return {v.x, v.y};
 }
 
-// src_idx == nullptr: record i is query i (round 1); otherwise the round-2 list (kPadIdx = padding slot)
+// One CTA per tile t.  Round 1 (seg == nullptr): the tile's records are queries [4096 t, 4096 t + 4096), idx = i.
+// Round 2: the tile's records are its misses, seg[t] = {first slot, count} in the round-2 list (src_idx = their idx).
+// table[t * n_bins + b] = {first slot, count} of the tile's run in bin b of the bin-major record arrays.
 template <int W>
-__global__ void __launch_bounds__(kSortThreads, 1)
-bin_scatter_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ src_idx, uint64_t n_records_arg,
-                   const uint64_t* __restrict__ mstart, uint32_t n_ranges, uint32_t n_bins, const uint32_t* __restrict__ meta1,
-                   uint32_t* __restrict__ cursor, uint64_t* __restrict__ rec_kmer, uint64_t* __restrict__ rec_meta) {
+__global__ void __launch_bounds__(kSortThreads, 2)
+bin_scatter_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ src_idx, const uint2* __restrict__ seg,
+                   uint64_t n_queries, uint32_t n_tiles, uint32_t n_bins, const uint32_t* __restrict__ meta1,
+                   uint32_t* __restrict__ cursor, uint64_t* __restrict__ rec_kmer, uint64_t* __restrict__ rec_meta,
+                   uint2* __restrict__ table) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t* s_kmer = reinterpret_cast<uint64_t*>(smem);                        // kSortTile * W words
-    uint64_t* s_meta = s_kmer + (size_t)kSortTile * W;                           // kSortTile
-    uint32_t* hist = reinterpret_cast<uint32_t*>(s_meta + kSortTile);            // n_bins
+    uint64_t* s_kmer = reinterpret_cast<uint64_t*>(smem);                        // kOutTile * W words
+    uint64_t* s_meta = s_kmer + (size_t)kOutTile * W;                            // kOutTile
+    uint32_t* hist = reinterpret_cast<uint32_t*>(s_meta + kOutTile);             // n_bins
     uint32_t* toff = hist + n_bins;                                              // n_bins
     uint32_t* gbase = toff + n_bins;                                             // n_bins
     uint32_t* scratch = gbase + n_bins;                                          // kSortThreads / 32 + 1
-    __shared__ uint32_t s_range;
-    const uint64_t n_records = mstart ? mstart[n_ranges] : n_records_arg;
-    const uint64_t n_tiles = (n_records + kSortTile - 1) / kSortTile;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t first;
+        uint32_t cnt;
+        if (seg) { const uint2 sg = seg[tile]; first = sg.x; cnt = sg.y; }
+        else { first = (uint64_t)tile * kOutTile; cnt = (uint32_t)(n_queries - first < (uint64_t)kOutTile ? n_queries - first : kOutTile); }
         for (uint32_t b = threadIdx.x; b < n_bins; b += kSortThreads) hist[b] = 0;
-        if (threadIdx.x == 0) s_range = range_of_tile(tile * kSortTile, mstart, n_ranges);
         __syncthreads();
         uint32_t meta[kSortItems], rank[kSortItems];
 #pragma unroll
         for (int t = 0; t < kSortItems; ++t) {
-            const uint64_t i = tile * kSortTile + (uint64_t)t * kSortThreads + threadIdx.x;
-            meta[t] = 0xffffffffu;
-            if (i < n_records && (!src_idx || src_idx[i] != kPadIdx)) meta[t] = meta1[i];
-            rank[t] = meta[t] != 0xffffffffu ? atomicAdd(&hist[meta[t] & 0xffffu], 1u) : 0u;
+            const uint32_t o = (uint32_t)t * kSortThreads + threadIdx.x;
+            meta[t] = o < cnt ? meta1[first + o] : 0xffffffffu;
+            rank[t] = o < cnt ? atomicAdd(&hist[meta[t] & 0xffffu], 1u) : 0u;
         }
         __syncthreads();
-        // tile-local offsets of the bins (n_bins <= kSortThreads) + one global reservation per (tile, bin)
-        const uint32_t mine = threadIdx.x < n_bins ? hist[threadIdx.x] : 0;
-        const uint32_t ex = cta_exclusive_scan<kSortThreads>(mine, scratch);
-        if (threadIdx.x < n_bins) {
-            toff[threadIdx.x] = ex;
-            gbase[threadIdx.x] = mine ? atomicAdd(&cursor[(uint64_t)s_range * n_bins + threadIdx.x], mine) : 0;
+        // tile-local offsets of the bins + one global reservation per (tile, bin)
+        const uint32_t r = (uint32_t)(((uint64_t)tile * kOutTile) >> kRangeShift);
+        for (uint32_t b0 = 0; b0 < n_bins; b0 += kSortThreads) {                 // n_bins <= 1024: at most two sweeps
+            const uint32_t b = b0 + threadIdx.x;
+            const uint32_t mine = b < n_bins ? hist[b] : 0;
+            const uint32_t ex = cta_exclusive_scan<kSortThreads>(mine, scratch);
+            const uint32_t carry = b0 ? toff[b0 - 1] + hist[b0 - 1] : 0;
+            if (b < n_bins) {
+                toff[b] = carry + ex;
+                const uint32_t g = mine ? atomicAdd(&cursor[(uint64_t)r * n_bins + b], mine) : 0;
+                gbase[b] = g;
+                table[(uint64_t)tile * n_bins + b] = make_uint2(g, mine);
+            }
+            __syncthreads();
         }
-        const uint32_t total = scratch[kSortThreads / 32];
-        __syncthreads();
 #pragma unroll
         for (int t = 0; t < kSortItems; ++t) {
-            if (meta[t] == 0xffffffffu) continue;
-            const uint64_t i = tile * kSortTile + (uint64_t)t * kSortThreads + threadIdx.x;
+            const uint32_t o = (uint32_t)t * kSortThreads + threadIdx.x;
+            if (o >= cnt) continue;
             const uint32_t bin = meta[t] & 0xffffu, p = toff[bin] + rank[t];
-            const uint32_t idx = src_idx ? src_idx[i] : (uint32_t)i;
-            store_plain(s_kmer, p, load_kmer<W>(kmers, i));
+            const uint32_t idx = src_idx ? src_idx[first + o] : (uint32_t)(first + o);
+            store_plain(s_kmer, p, load_kmer<W>(kmers, first + o));
             s_meta[p] = (uint64_t)idx | ((uint64_t)(meta[t] >> 16) << 32) | ((uint64_t)bin << 40);
         }
         __syncthreads();
-        for (uint32_t p = threadIdx.x; p < total; p += kSortThreads) {     // consecutive p of a bin -> consecutive slots
+        for (uint32_t p = threadIdx.x; p < cnt; p += kSortThreads) {          // consecutive p of a bin -> consecutive slots
             const uint64_t m = s_meta[p];
             const uint32_t bin = (uint32_t)(m >> 40) & 0xffffu;
             const uint64_t dest = (uint64_t)gbase[bin] + (p - toff[bin]);
@@ -264,7 +248,7 @@ template <int W, bool CANON>
 __global__ void __launch_bounds__(kBlock, 6)
 lookup_binned_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ rec_kmer, const uint64_t* __restrict__ rec_meta,
                      uint32_t n_bins, const uint32_t* __restrict__ bin_start, const BinRegion* __restrict__ regions, uint32_t lookahead,
-                     uint64_t* __restrict__ res_id, uint32_t* __restrict__ miss_counts, unsigned long long* __restrict__ claim) {
+                     uint64_t* __restrict__ res_id, unsigned long long* __restrict__ claim) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_records = bin_start[n_bins];
     for (;;) {
@@ -290,161 +274,166 @@ lookup_binned_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __r
 #pragma unroll 1
         for (int t = 0; t < kClaimItems; ++t) {
             const uint64_t j = first + (uint64_t)t * 32 + lane;
-            const bool active = j < n_records;
-            bool found = false;
-            uint64_t meta = 0;
+            if (j >= n_records) break;
+            const Kmer<W> x = load_kmer<W>(rec_kmer, j);
+            const uint64_t meta = __ldcs(rec_meta + j);
+            const uint32_t pos = (uint32_t)(meta >> 32) & 63u;
+            bool found;
             LookupResult res;
-            res.kmer_id = ~0ull;
-            if (active) {
-                const Kmer<W> x = load_kmer<W>(rec_kmer, j);
-                meta = __ldcs(rec_meta + j);
-                const uint32_t pos = (uint32_t)(meta >> 32) & 63u;
-                if (CANON) {
-                    const Kmer<W> xr = kmer_rc(x, ix.k);
-                    const bool from_rc = (meta >> 38) & 1;
-                    Minimizer mi{kmer_bits_at(from_rc ? xr : x, 2 * pos) & ix.mmer_mask, pos};
+            if (CANON) {
+                const Kmer<W> xr = kmer_rc(x, ix.k);
+                const bool from_rc = (meta >> 38) & 1;
+                Minimizer mi{kmer_bits_at(from_rc ? xr : x, 2 * pos) & ix.mmer_mask, pos};
+                found = lookup_canonical_with<W, false, false, true>(ix, x, xr, mi, res);
+                if (!found && ((meta >> 39) & 1)) {       // tie: the rc info is tried second (dictionary.cpp:35-41)
+                    mi = compute_minimizer(ix, xr);
                     found = lookup_canonical_with<W, false, false, true>(ix, x, xr, mi, res);
-                    if (!found && ((meta >> 39) & 1)) {       // tie: the rc info is tried second (dictionary.cpp:35-41)
-                        mi = compute_minimizer(ix, xr);
-                        found = lookup_canonical_with<W, false, false, true>(ix, x, xr, mi, res);
-                    }
-                } else {
-                    const Minimizer mi{kmer_bits_at(x, 2 * pos) & ix.mmer_mask, pos};
-                    found = lookup_regular_with<W, false, false, true>(ix, x, mi, res);
                 }
-                __stcs(res_id + j, found ? res.kmer_id : ~0ull);
+            } else {
+                const Minimizer mi{kmer_bits_at(x, 2 * pos) & ix.mmer_mask, pos};
+                found = lookup_regular_with<W, false, false, true>(ix, x, mi, res);
             }
-            if (miss_counts) {                                   // warp-uniform
-                const bool miss = active && !found;
-                const uint32_t s = miss ? ((uint32_t)meta >> kRangeShift) * n_bins + (uint32_t)((meta >> 40) & 0xffffu) : 0xffffffffu;
-                const uint32_t peers = __match_any_sync(0xffffffffu, s);
-                if (miss && lane == (uint32_t)__ffs(peers) - 1) atomicAdd(&miss_counts[s], (uint32_t)__popc(peers));
-            }
-        }
-    }
-}
-
-// ---- between B and C of round 1 (one CTA): slots of the round-2 list -------------------------------
-__global__ void __launch_bounds__(kBlock)
-miss_scan_kernel(Control c, uint32_t n_ranges, uint32_t n_bins) {
-    for (uint32_t r = threadIdx.x; r < n_ranges; r += kBlock) {
-        uint64_t s = 0;
-        for (uint32_t b = 0; b < n_bins; ++b) s += c.miss_counts[(uint64_t)r * n_bins + b];
-        c.mstart[r] = s;                                      // the range's total for now
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t run = 0;
-        for (uint32_t r = 0; r < n_ranges; ++r) {
-            const uint64_t t = c.mstart[r];
-            c.mstart[r] = run;
-            run += (t + kSortTile - 1) / kSortTile * kSortTile;    // every range starts on a scatter-tile boundary
-        }
-        c.mstart[n_ranges] = run;
-    }
-    __syncthreads();
-    for (uint32_t r = threadIdx.x; r < n_ranges; r += kBlock) {
-        uint32_t run = (uint32_t)c.mstart[r];
-        for (uint32_t b = 0; b < n_bins; ++b) {
-            const uint64_t s = (uint64_t)r * n_bins + b;
-            c.mcursor[s] = run;
-            run += c.miss_counts[s];
+            __stcs(res_id + j, found ? res.kmer_id : ~0ull);
         }
     }
 }
 
 // ---- C --------------------------------------------------------------------------------------------
-// MODE 0: u64 ids, 2: membership bytes, 3: u32 ids.  SECOND: a round follows -- misses go to its list
-// (reverse-complemented, with their bin in that round: next_meta1 / next_counts) instead of the output.
+// MODE 0: u64 ids, 2: membership bytes, 3: u32 ids
+template <int MODE> struct OutT;
+template <> struct OutT<0> { using type = uint64_t; };
+template <> struct OutT<2> { using type = uint8_t; };
+template <> struct OutT<3> { using type = uint32_t; };
+template <int MODE>
+__device__ __forceinline__ typename OutT<MODE>::type out_value(uint64_t id) {
+    if (MODE == 2) return id != ~0ull;
+    return (typename OutT<MODE>::type)id;                 // u32: "not found" truncates to UINT32_MAX
+}
+
+// C1: one CTA per tile; warps walk the tile's runs (one per bin).  SECOND: a round follows -- misses go to
+// its list (reverse-complemented, with their bin in that round) and read "not found" until C2 patches them.
 template <int W, int MODE, bool SECOND>
 __global__ void __launch_bounds__(kBlock)
-unpermute_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ rec_kmer, const uint64_t* __restrict__ rec_meta,
-                 const uint64_t* __restrict__ res_id, Control c, uint32_t n_ranges, uint32_t n_bins, uint32_t bin_shift,
-                 void* __restrict__ out, uint64_t* __restrict__ miss_kmer, uint32_t* __restrict__ miss_idx,
-                 uint32_t* __restrict__ next_meta1, uint32_t* __restrict__ next_counts) {
-    extern __shared__ uint32_t hist[];                    // SECOND: n_bins counters of the chunk's misses per round-2 bin
-    __shared__ uint32_t s_run, s_first, s_cnt, s_slot, scratch[kBlock / 32 + 1];
-    const uint64_t runs = (uint64_t)n_ranges * n_bins;
-    const uint32_t n_chunks = c.chunk_start[runs];
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long ch = atomicAdd(c.claims + 1, 1ull);
-            if (ch >= n_chunks) s_cnt = 0xffffffffu;
-            else {
-                uint64_t lo = 0, hi = runs;                 // sub-run of the chunk: largest s with chunk_start[s] <= ch
-                while (hi - lo > 1) { const uint64_t mid = (lo + hi) / 2; if (c.chunk_start[mid] <= ch) lo = mid; else hi = mid; }
-                // sub-runs without records share a chunk_start with their successor: take the last one of the tie
-                const uint32_t off = ((uint32_t)ch - c.chunk_start[lo]) * kChunk, cnt = c.counts[lo];
-                s_run = (uint32_t)lo;
-                s_first = c.base[lo] + off;
-                s_cnt = cnt - off < (uint32_t)kChunk ? cnt - off : (uint32_t)kChunk;
-            }
-        }
+gather_tile_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ rec_kmer, const uint64_t* __restrict__ rec_meta,
+                   const uint64_t* __restrict__ res_id, const uint2* __restrict__ table, uint64_t n_queries, uint32_t n_tiles,
+                   uint32_t n_bins, uint32_t bin_shift, void* __restrict__ out, uint64_t* __restrict__ miss_kmer,
+                   uint32_t* __restrict__ miss_idx, uint32_t* __restrict__ miss_meta1, uint2* __restrict__ seg,
+                   uint32_t* __restrict__ next_counts, unsigned long long* __restrict__ miss_total) {
+    using T = typename OutT<MODE>::type;
+    extern __shared__ __align__(16) uint8_t smem[];
+    T* image = reinterpret_cast<T*>(smem);                                       // kOutTile results
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)kOutTile * sizeof(T));   // SECOND: n_bins
+    __shared__ uint32_t warp_miss[kBlock / 32 + 1], s_seg;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t first = (uint64_t)tile * kOutTile;
+        const uint32_t cnt = (uint32_t)(n_queries - first < (uint64_t)kOutTile ? n_queries - first : kOutTile);
         if (SECOND) for (uint32_t b = threadIdx.x; b < n_bins; b += kBlock) hist[b] = 0;
-        __syncthreads();
-        if (s_cnt == 0xffffffffu) break;
-        const uint32_t first = s_first, cnt = s_cnt, run = s_run;
-        uint32_t n_miss = 0, idxs[kChunkItems];
-        bool miss[kChunkItems];
-#pragma unroll
-        for (int t = 0; t < kChunkItems; ++t) {
-            const uint32_t o = (uint32_t)t * kBlock + threadIdx.x;
-            miss[t] = false;
-            idxs[t] = 0;
-            if (o < cnt) {
-                const uint64_t j = (uint64_t)first + o;
+        uint32_t my_miss = 0;
+        for (uint32_t b = wid; b < n_bins; b += kBlock / 32) {
+            const uint2 run = table[(uint64_t)tile * n_bins + b];
+            for (uint32_t o = lane; o < run.y; o += 32) {
+                const uint64_t j = (uint64_t)run.x + o;
                 const uint64_t id = __ldcs(res_id + j);
                 const uint32_t idx = (uint32_t)__ldcs(rec_meta + j);
-                const bool hit = id != ~0ull;
-                idxs[t] = idx;
-                if (hit || !SECOND) {
-                    if (MODE == 2) static_cast<uint8_t*>(out)[idx] = hit;
-                    else if (MODE == 3) static_cast<uint32_t*>(out)[idx] = (uint32_t)id;   // not found: UINT32_MAX
-                    else static_cast<uint64_t*>(out)[idx] = id;
-                } else { miss[t] = true; ++n_miss; }
+                image[idx - (uint32_t)first] = out_value<MODE>(id);
+                if (SECOND && id == ~0ull) ++my_miss;
             }
         }
         if (SECOND) {
-            // slots of this chunk's misses: one reservation per chunk from the sub-run's cursor
-            const uint32_t before = cta_exclusive_scan<kBlock>(n_miss, scratch);
-            if (threadIdx.x == kBlock - 1) s_slot = (before + n_miss) ? atomicAdd(&c.mcursor[run], before + n_miss) : 0;
+            // slots of the tile's misses in the round-2 list: one reservation per tile, warps in order
+            for (int o = 16; o > 0; o >>= 1) my_miss += __shfl_down_sync(0xffffffffu, my_miss, o);
+            if (lane == 0) warp_miss[wid] = my_miss;
             __syncthreads();
-            uint32_t slot = s_slot + before;
-#pragma unroll
-            for (int t = 0; t < kChunkItems; ++t) {
-                if (!miss[t]) continue;
-                const uint64_t j = (uint64_t)first + (uint32_t)t * kBlock + threadIdx.x;
-                const Kmer<W> xr = kmer_rc(load_kmer<W>(rec_kmer, j), ix.k);               // src/dictionary.cpp:72
-                const uint32_t meta = bin_meta_of<W, false>(ix, xr, bin_shift);
-                store_kmer(miss_kmer, slot, xr);
-                miss_idx[slot] = idxs[t];
-                next_meta1[slot] = meta;
-                atomicAdd(&hist[meta & 0xffffu], 1u);
-                ++slot;
+            if (threadIdx.x == 0) {
+                uint32_t run = 0;
+                for (int w = 0; w < kBlock / 32; ++w) { const uint32_t t = warp_miss[w]; warp_miss[w] = run; run += t; }
+                warp_miss[kBlock / 32] = run;
+                s_seg = run ? (uint32_t)atomicAdd(miss_total, (unsigned long long)run) : 0;
+                seg[tile] = make_uint2(s_seg, run);
             }
             __syncthreads();
-            const uint32_t r = run / n_bins;
+            if (warp_miss[kBlock / 32]) {                         // CTA-uniform
+                uint32_t slot = s_seg + warp_miss[wid];
+                for (uint32_t b = wid; b < n_bins; b += kBlock / 32) {
+                    const uint2 run = table[(uint64_t)tile * n_bins + b];
+                    for (uint32_t o0 = 0; o0 < run.y; o0 += 32) {
+                        const uint32_t o = o0 + lane;
+                        const uint64_t j = (uint64_t)run.x + o;
+                        const bool miss = o < run.y && res_id[j] == ~0ull;
+                        const uint32_t mask = __ballot_sync(0xffffffffu, miss);
+                        if (miss) {
+                            const uint32_t at = slot + __popc(mask & ((1u << lane) - 1));
+                            const Kmer<W> xr = kmer_rc(load_plain(rec_kmer, j, (Kmer<W>*)nullptr), ix.k);     // src/dictionary.cpp:72
+                            const uint32_t meta = bin_meta_of<W, false>(ix, xr, bin_shift);
+                            store_plain(miss_kmer, at, xr);
+                            miss_idx[at] = (uint32_t)rec_meta[j];
+                            miss_meta1[at] = meta;
+                            atomicAdd(&hist[meta & 0xffffu], 1u);
+                        }
+                        slot += __popc(mask);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // the tile's results leave as one coalesced block
+        T* dst = static_cast<T*>(out) + first;
+        for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) dst[i] = image[i];
+        if (SECOND) {
+            const uint32_t r = (uint32_t)(first >> kRangeShift);
             for (uint32_t b = threadIdx.x; b < n_bins; b += kBlock)
                 if (hist[b]) atomicAdd(&next_counts[(uint64_t)r * n_bins + b], hist[b]);
         }
+        __syncthreads();
+    }
+}
+
+// C2: one CTA per tile that had misses: read the ids block back, patch the round-2 results in, store it
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+patch_tile_kernel(const uint64_t* __restrict__ rec_meta, const uint64_t* __restrict__ res_id, const uint2* __restrict__ table,
+                  const uint2* __restrict__ seg, uint64_t n_queries, uint32_t n_tiles, uint32_t n_bins, void* __restrict__ out) {
+    using T = typename OutT<MODE>::type;
+    extern __shared__ __align__(16) uint8_t smem[];
+    T* image = reinterpret_cast<T*>(smem);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (seg[tile].y == 0) continue;                       // CTA-uniform: nothing of this tile went to round 2
+        const uint64_t first = (uint64_t)tile * kOutTile;
+        const uint32_t cnt = (uint32_t)(n_queries - first < (uint64_t)kOutTile ? n_queries - first : kOutTile);
+        T* dst = static_cast<T*>(out) + first;
+        for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) image[i] = dst[i];
+        __syncthreads();
+        for (uint32_t b = wid; b < n_bins; b += kBlock / 32) {
+            const uint2 run = table[(uint64_t)tile * n_bins + b];
+            for (uint32_t o = lane; o < run.y; o += 32) {
+                const uint64_t j = (uint64_t)run.x + o;
+                image[(uint32_t)__ldcs(rec_meta + j) - (uint32_t)first] = out_value<MODE>(__ldcs(res_id + j));
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) dst[i] = image[i];
+        __syncthreads();
     }
 }
 
 uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 struct Plan {                      // carve-up of the scratch buffer for a batch of n queries
-    uint32_t n_ranges, n_bins;
-    uint64_t cap;                  // records any array holds: n + one scatter tile of padding per range
+    uint32_t n_ranges, n_bins, n_tiles;
+    uint64_t cap;                  // records any array holds
     uint64_t runs;                 // n_ranges * n_bins
-    uint64_t off_meta1, off_rec_kmer, off_rec_meta, off_res, off_miss_kmer, off_miss_idx, off_ctl[2], ctl_bytes, total;
+    uint64_t off_meta1, off_rec_kmer, off_rec_meta, off_res, off_miss_kmer, off_miss_idx, off_miss_meta1, off_table, off_seg,
+        off_ctl[2], ctl_bytes, total;
 };
 
 Plan make_plan(uint32_t kmer_words, uint32_t n_bins, uint64_t n) {
     Plan p{};
     p.n_bins = n_bins;
     p.n_ranges = (uint32_t)((n + (1ull << kRangeShift) - 1) >> kRangeShift);
-    p.cap = align_up(n, kSortTile) + (uint64_t)p.n_ranges * kSortTile;
+    p.n_tiles = (uint32_t)((n + kOutTile - 1) / kOutTile);
+    p.cap = align_up(n, kOutTile);
     p.runs = (uint64_t)p.n_ranges * n_bins;
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) { const uint64_t at = o; o += align_up(bytes, 256); return at; };
@@ -454,8 +443,11 @@ Plan make_plan(uint32_t kmer_words, uint32_t n_bins, uint64_t n) {
     p.off_res = take(p.cap * 8);
     p.off_miss_kmer = take(p.cap * 8 * kmer_words);
     p.off_miss_idx = take(p.cap * 4);
-    // control block: 6 arrays of runs (+1) u32, bin_start (n_bins + 1), mstart (n_ranges + 1, u64), claims (2 x u64)
-    p.ctl_bytes = align_up((6 * p.runs + 1 + n_bins + 1) * 4, 8) + (p.n_ranges + 1) * 8 + 16;
+    p.off_miss_meta1 = take(p.cap * 4);
+    p.off_table = take((uint64_t)p.n_tiles * n_bins * 8);
+    p.off_seg = take((uint64_t)p.n_tiles * 8);
+    // control block: counts, cursor (runs each), bin_start (n_bins + 1), claims (2 x u64)
+    p.ctl_bytes = align_up((2 * p.runs + n_bins + 1) * 4, 8) + 16;
     p.off_ctl[0] = take(p.ctl_bytes);
     p.off_ctl[1] = take(p.ctl_bytes);
     p.total = o;
@@ -465,17 +457,13 @@ Plan make_plan(uint32_t kmer_words, uint32_t n_bins, uint64_t n) {
 Control control_at(uint8_t* base, const Plan& p) {
     Control c{};
     uint32_t* u = reinterpret_cast<uint32_t*>(base);
-    c.counts = u; c.base = u + p.runs; c.cursor = u + 2 * p.runs; c.miss_counts = u + 3 * p.runs; c.mcursor = u + 4 * p.runs;
-    c.chunk_start = u + 5 * p.runs;                        // runs + 1 entries
-    c.bin_start = u + 6 * p.runs + 1;
-    uint8_t* q = base + align_up((6 * p.runs + 1 + p.n_bins + 1) * 4, 8);
-    c.mstart = reinterpret_cast<uint64_t*>(q);
-    c.claims = reinterpret_cast<unsigned long long*>(q + (p.n_ranges + 1) * 8);
+    c.counts = u; c.cursor = u + p.runs; c.bin_start = u + 2 * p.runs;
+    c.claims = reinterpret_cast<unsigned long long*>(base + align_up((2 * p.runs + p.n_bins + 1) * 4, 8));
     return c;
 }
 
 size_t scatter_smem_bytes(uint32_t kmer_words, uint32_t n_bins) {
-    return (size_t)kSortTile * 8 * (kmer_words + 1) + (3 * (size_t)n_bins + kSortThreads / 32 + 1) * 4;
+    return (size_t)kOutTile * 8 * (kmer_words + 1) + (3 * (size_t)n_bins + kSortThreads / 32 + 1) * 4;
 }
 
 }  // namespace
@@ -489,7 +477,7 @@ uint64_t binned_scratch_bytes(const DeviceIndex& ix, const LaunchCtx& ctx, uint6
 cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, const uint64_t* queries, uint64_t n, bool check_rc,
                                  uint64_t* ids, uint32_t* ids32, uint8_t* member, void* scratch, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    if (n > binned_max_batch() || !ctx.bins.n_bins || ctx.bins.n_bins > (uint32_t)kSortThreads) return cudaErrorInvalidValue;
+    if (n > binned_max_batch() || !ctx.bins.n_bins || ctx.bins.n_bins > kMaxBins) return cudaErrorInvalidValue;
     const Plan p = make_plan(ix.kmer_words, ctx.bins.n_bins, n);
     uint8_t* s = static_cast<uint8_t*>(scratch);
     uint32_t* meta1 = reinterpret_cast<uint32_t*>(s + p.off_meta1);
@@ -498,23 +486,23 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
     uint64_t* res = reinterpret_cast<uint64_t*>(s + p.off_res);
     uint64_t* miss_kmer = reinterpret_cast<uint64_t*>(s + p.off_miss_kmer);
     uint32_t* miss_idx = reinterpret_cast<uint32_t*>(s + p.off_miss_idx);
+    uint32_t* miss_meta1 = reinterpret_cast<uint32_t*>(s + p.off_miss_meta1);
+    uint2* table = reinterpret_cast<uint2*>(s + p.off_table);
+    uint2* seg = reinterpret_cast<uint2*>(s + p.off_seg);
     const bool canon = ix.canonical != 0, two_rounds = !canon && check_rc;
     const int mode = member ? 2 : (ids32 ? 3 : 0);
     void* out = member ? static_cast<void*>(member) : ids32 ? static_cast<void*>(ids32) : static_cast<void*>(ids);
-    const uint32_t nb = p.n_bins, nr = p.n_ranges, shift = ctx.bins.bin_shift;
+    const uint32_t nb = p.n_bins, nr = p.n_ranges, nt = p.n_tiles, shift = ctx.bins.bin_shift;
     const BinRegion* regions = ctx.bins.prefetch ? ctx.bins.regions : nullptr;
     const int sm = ctx.sm_count;
     const bool w1 = ix.kmer_words == 1;
     cudaError_t e = cudaMemsetAsync(s + p.off_ctl[0], 0, two_rounds ? 2 * align_up(p.ctl_bytes, 256) : p.ctl_bytes, stream);
     if (e != cudaSuccess) return e;
-    if (two_rounds) {
-        e = cudaMemsetAsync(miss_idx, 0xff, p.cap * 4, stream);        // every slot is padding until a miss lands in it
-        if (e != cudaSuccess) return e;
-    }
     const size_t hist_bytes = nb * sizeof(uint32_t), sort_smem = scatter_smem_bytes(ix.kmer_words, nb);
+    const size_t out_elem = mode == 2 ? 1 : mode == 3 ? 4 : 8;
     // opt-in shared memory above 48 KB is a per-device function attribute: set it on every call (microseconds)
-    cudaFuncSetAttribute(bin_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1, kSortThreads));
-    cudaFuncSetAttribute(bin_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(2, kSortThreads));
+    cudaFuncSetAttribute(bin_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(1, kMaxBins));
+    cudaFuncSetAttribute(bin_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_bytes(2, kMaxBins));
     auto cfg_launch = [&](auto kernel, int grid, int block, size_t smem, auto... args) -> cudaError_t {
         g_launches.fetch_add(1);
         cudaLaunchConfig_t cfg{};
@@ -533,7 +521,8 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
         return cudaLaunchKernelEx(&cfg, kernel, args...);
     };
     const Control c0 = control_at(s + p.off_ctl[0], p), c1 = control_at(s + p.off_ctl[1], p);
-    // ---- A1 (round 1 only: round 2's bins are computed by C of round 1) ----
+    const int tile_grid = (int)std::min<uint64_t>(nt, (uint64_t)sm * 8);
+    // ---- A1 (round 1 only: round 2's bins are computed by C1) ----
     {
         const int grid = (int)std::min<uint64_t>((n + kTile - 1) / kTile, (uint64_t)sm * 8);
         if (canon) e = w1 ? cfg_launch(bin_count_kernel<1, true>, grid, kBlock, hist_bytes, ix, queries, n, nb, shift, meta1, c0.counts)
@@ -545,36 +534,37 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
     for (int round = 0; round < (two_rounds ? 2 : 1); ++round) {
         const Control c = round ? c1 : c0;
         const bool r2 = round == 1, second = two_rounds && !r2;
+        e = cfg_launch(bin_scan_kernel, 1, (int)kMaxBins, 0, c, nr, nb);
+        if (e != cudaSuccess) return e;
         const uint64_t* src_kmer = r2 ? miss_kmer : queries;
         const uint32_t* src_idx = r2 ? miss_idx : nullptr;
-        const uint64_t* mstart = r2 ? c0.mstart : nullptr;
-        const uint64_t bound = r2 ? p.cap : n;              // round 2's exact length lives on the device (mstart[n_ranges])
-        e = cfg_launch(bin_scan_kernel, 1, kSortThreads, (nb + 1 + kSortThreads / 32 + 1) * sizeof(uint32_t), c, nr, nb);
+        const uint32_t* src_meta1 = r2 ? miss_meta1 : meta1;
+        const uint2* src_seg = r2 ? seg : nullptr;
+        const int sgrid = (int)std::min<uint64_t>(nt, (uint64_t)sm * 2);
+        e = w1 ? cfg_launch(bin_scatter_kernel<1>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, table)
+               : cfg_launch(bin_scatter_kernel<2>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, table);
         if (e != cudaSuccess) return e;
-        const int sgrid = (int)std::min<uint64_t>((bound + kSortTile - 1) / kSortTile, (uint64_t)sm);
-        e = w1 ? cfg_launch(bin_scatter_kernel<1>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, n, mstart, nr, nb, (const uint32_t*)meta1, c.cursor, rec_kmer, rec_meta)
-               : cfg_launch(bin_scatter_kernel<2>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, n, mstart, nr, nb, (const uint32_t*)meta1, c.cursor, rec_kmer, rec_meta);
-        if (e != cudaSuccess) return e;
-        uint32_t* miss_counts = second ? c.miss_counts : nullptr;
         const int lgrid = sm * 6;
 #define SSHASH_LOOKUP_BINNED(W, CANON) \
-        cfg_launch(lookup_binned_kernel<W, CANON>, lgrid, kBlock, 0, ix, (const uint64_t*)rec_kmer, (const uint64_t*)rec_meta, nb, (const uint32_t*)c.bin_start, regions, ctx.bins.lookahead, res, miss_counts, c.claims)
+        cfg_launch(lookup_binned_kernel<W, CANON>, lgrid, kBlock, 0, ix, (const uint64_t*)rec_kmer, (const uint64_t*)rec_meta, nb, (const uint32_t*)c.bin_start, regions, ctx.bins.lookahead, res, c.claims)
         if (canon) e = w1 ? SSHASH_LOOKUP_BINNED(1, true) : SSHASH_LOOKUP_BINNED(2, true);
         else e = w1 ? SSHASH_LOOKUP_BINNED(1, false) : SSHASH_LOOKUP_BINNED(2, false);
 #undef SSHASH_LOOKUP_BINNED
         if (e != cudaSuccess) return e;
-        if (second) {
-            e = cfg_launch(miss_scan_kernel, 1, kBlock, 0, c, nr, nb);
-            if (e != cudaSuccess) return e;
+        if (!r2) {
+#define SSHASH_GATHER(W, MODE, SECOND) \
+            cfg_launch(gather_tile_kernel<W, MODE, SECOND>, tile_grid, kBlock, kOutTile * out_elem + (SECOND ? hist_bytes : 0), ix, (const uint64_t*)rec_kmer, (const uint64_t*)rec_meta, (const uint64_t*)res, (const uint2*)table, n, nt, nb, shift, out, miss_kmer, miss_idx, miss_meta1, seg, c1.counts, c0.claims + 1)
+#define SSHASH_GATHER_MODE(W, SECOND) (mode == 2 ? SSHASH_GATHER(W, 2, SECOND) : mode == 3 ? SSHASH_GATHER(W, 3, SECOND) : SSHASH_GATHER(W, 0, SECOND))
+            if (second) e = w1 ? SSHASH_GATHER_MODE(1, true) : SSHASH_GATHER_MODE(2, true);
+            else e = w1 ? SSHASH_GATHER_MODE(1, false) : SSHASH_GATHER_MODE(2, false);
+#undef SSHASH_GATHER_MODE
+#undef SSHASH_GATHER
+        } else {
+#define SSHASH_PATCH(MODE) \
+            cfg_launch(patch_tile_kernel<MODE>, tile_grid, kBlock, kOutTile * out_elem, (const uint64_t*)rec_meta, (const uint64_t*)res, (const uint2*)table, (const uint2*)seg, n, nt, nb, out)
+            e = mode == 2 ? SSHASH_PATCH(2) : mode == 3 ? SSHASH_PATCH(3) : SSHASH_PATCH(0);
+#undef SSHASH_PATCH
         }
-        const int ugrid = (int)std::min<uint64_t>((bound + kChunk - 1) / kChunk + p.runs, (uint64_t)sm * 8);
-#define SSHASH_UNPERMUTE(W, MODE, SECOND) \
-        cfg_launch(unpermute_kernel<W, MODE, SECOND>, ugrid, kBlock, SECOND ? hist_bytes : 0, ix, (const uint64_t*)rec_kmer, (const uint64_t*)rec_meta, (const uint64_t*)res, c, nr, nb, shift, out, miss_kmer, miss_idx, meta1, c1.counts)
-#define SSHASH_UNPERMUTE_MODE(W, SECOND) (mode == 2 ? SSHASH_UNPERMUTE(W, 2, SECOND) : mode == 3 ? SSHASH_UNPERMUTE(W, 3, SECOND) : SSHASH_UNPERMUTE(W, 0, SECOND))
-        if (second) e = w1 ? SSHASH_UNPERMUTE_MODE(1, true) : SSHASH_UNPERMUTE_MODE(2, true);
-        else e = w1 ? SSHASH_UNPERMUTE_MODE(1, false) : SSHASH_UNPERMUTE_MODE(2, false);
-#undef SSHASH_UNPERMUTE_MODE
-#undef SSHASH_UNPERMUTE
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

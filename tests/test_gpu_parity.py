@@ -624,6 +624,18 @@ def test_concurrent_batches_on_one_handle(dicts):
     assert not errors, errors
 
 
+@pytest.mark.parametrize("name", ["se_k31_m13", "sal100_k31_m7_canon", "sal100_k31_m7_reg", "twins_k31_m13_reg"])
+def test_streaming_replay_path_equals_the_shortcuts(name):
+    """SSHASH_GPU_ASSUME_DISTINCT=0 forces the literal replay of the reference's state machine (the path
+    indexes with duplicated k-mers / rc twins take): same ids and counters as the goldens."""
+    g = golden(name)
+    d = _open_with_env(g.index, {"SSHASH_GPU_ASSUME_DISTINCT": "0"}, device=0, max_k=g.max_k)
+    sids, rep = d.streaming_batch(g.z["read_bases"], g.z["read_offsets"])
+    assert (sids == g.z["stream_ids"]).all()
+    assert rep == dict(zip(REPORT_KEYS, g.z["stream_report"].tolist()))
+    d.close()
+
+
 def test_sharded_lookup_with_peer_store_gather_two_gpus():
     """N > 1: every rank's lookup kernel stores its ids straight into rank 0's gathered vector through
     NVLink peer stores (sshash_b200.sharded, mode "peer"); rank 0 checks every slice against the
