@@ -21,13 +21,13 @@
 //   A2  bin_scan_kernel     exclusive scan in (bin, range) order -> every (range, bin) sub-run's slot
 //   A3  bin_scatter_kernel  one CTA per TILE of 4096 consecutive queries: the tile's records {k-mer, idx |
 //                           pos | bin} are sorted by bin in shared memory and leave as coalesced runs
-//                           (one global reservation per (tile, bin)); the run of every (tile, bin) is
-//                           recorded in a table so that the tile's results can be found again
+//                           (one global reservation per (tile, bin)); slot_of[] records where every record
+//                           of the tile went so that the tile's results can be found again
 //   B   lookup_binned_kernel  warps claim 128 consecutive records of the bin-major arrays; each record
 //                           is ONE pass of the reference's lookup with the minimizer given
 //                           (device_index.cuh); result ids stored in record order
-//   C1  gather_tile_kernel  one CTA per tile: the tile's results are collected from its <= n_bins runs
-//                           into a shared-memory image of ids[4096 t .. 4096 t + 4096) and stored as
+//   C1  gather_tile_kernel  one CTA per tile: the tile's results are collected through slot_of[] (reads run
+//                           along the tile's <= n_bins runs) into a shared-memory image of ids[4096 t .. 4096 t + 4096) and stored as
 //                           one coalesced block; misses of a regular index with check_reverse_complement
 //                           are appended, reverse-complemented, to the round-2 list (src/dictionary.cpp:71-76)
 //                           together with their round-2 bin (A1 of round 2 is fused in here)
@@ -161,13 +161,14 @@ __device__ __forceinline__ Kmer<2> load_plain(const uint64_t* in, uint64_t i, Km
 
 // One CTA per tile t.  Round 1 (seg == nullptr): the tile's records are queries [4096 t, 4096 t + 4096), idx = i.
 // Round 2: the tile's records are its misses, seg[t] = {first slot, count} in the round-2 list (src_idx = their idx).
-// table[t * n_bins + b] = {first slot, count} of the tile's run in bin b of the bin-major record arrays.
+// slot_of[first + p] = slot, in the bin-major record arrays, of the p-th record of the tile in bin order: the
+// way back for C (consecutive p of one bin are consecutive slots).
 template <int W>
-__global__ void __launch_bounds__(kSortThreads, 2)
+__global__ void __launch_bounds__(kSortThreads, W == 1 ? 3 : 2)
 bin_scatter_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ src_idx, const uint2* __restrict__ seg,
                    uint64_t n_queries, uint32_t n_tiles, uint32_t n_bins, const uint32_t* __restrict__ meta1,
                    uint32_t* __restrict__ cursor, uint64_t* __restrict__ rec_kmer, uint64_t* __restrict__ rec_meta,
-                   uint2* __restrict__ table) {
+                   uint32_t* __restrict__ slot_of) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* s_kmer = reinterpret_cast<uint64_t*>(smem);                        // kOutTile * W words
     uint64_t* s_meta = s_kmer + (size_t)kOutTile * W;                            // kOutTile
@@ -201,7 +202,6 @@ bin_scatter_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restric
                 toff[b] = carry + ex;
                 const uint32_t g = mine ? atomicAdd(&cursor[(uint64_t)r * n_bins + b], mine) : 0;
                 gbase[b] = g;
-                table[(uint64_t)tile * n_bins + b] = make_uint2(g, mine);
             }
             __syncthreads();
         }
@@ -221,6 +221,7 @@ bin_scatter_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restric
             const uint64_t dest = (uint64_t)gbase[bin] + (p - toff[bin]);
             store_plain(rec_kmer, dest, load_plain(s_kmer, p, (Kmer<W>*)nullptr));
             rec_meta[dest] = m;
+            slot_of[first + p] = (uint32_t)dest;
         }
         __syncthreads();
     }
@@ -310,12 +311,13 @@ __device__ __forceinline__ typename OutT<MODE>::type out_value(uint64_t id) {
     return (typename OutT<MODE>::type)id;                 // u32: "not found" truncates to UINT32_MAX
 }
 
-// C1: one CTA per tile; warps walk the tile's runs (one per bin).  SECOND: a round follows -- misses go to
-// its list (reverse-complemented, with their bin in that round) and read "not found" until C2 patches them.
+// C1: one CTA per tile, one thread per record of the tile in bin order (slot_of).  SECOND: a round follows --
+// misses go to its list (reverse-complemented, with their bin in that round) and read "not found" until
+// C2 patches them.
 template <int W, int MODE, bool SECOND>
 __global__ void __launch_bounds__(kBlock)
 gather_tile_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __restrict__ rec_kmer, const uint64_t* __restrict__ rec_meta,
-                   const uint64_t* __restrict__ res_id, const uint2* __restrict__ table, uint64_t n_queries, uint32_t n_tiles,
+                   const uint64_t* __restrict__ res_id, const uint32_t* __restrict__ slot_of, uint64_t n_queries, uint32_t n_tiles,
                    uint32_t n_bins, uint32_t bin_shift, void* __restrict__ out, uint64_t* __restrict__ miss_kmer,
                    uint32_t* __restrict__ miss_idx, uint32_t* __restrict__ miss_meta1, uint2* __restrict__ seg,
                    uint32_t* __restrict__ next_counts, unsigned long long* __restrict__ miss_total) {
@@ -323,56 +325,41 @@ gather_tile_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __res
     extern __shared__ __align__(16) uint8_t smem[];
     T* image = reinterpret_cast<T*>(smem);                                       // kOutTile results
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)kOutTile * sizeof(T));   // SECOND: n_bins
-    __shared__ uint32_t warp_miss[kBlock / 32 + 1], s_seg;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ uint32_t scratch[kBlock / 32 + 1], s_seg;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t first = (uint64_t)tile * kOutTile;
         const uint32_t cnt = (uint32_t)(n_queries - first < (uint64_t)kOutTile ? n_queries - first : kOutTile);
         if (SECOND) for (uint32_t b = threadIdx.x; b < n_bins; b += kBlock) hist[b] = 0;
         uint32_t my_miss = 0;
-        for (uint32_t b = wid; b < n_bins; b += kBlock / 32) {
-            const uint2 run = table[(uint64_t)tile * n_bins + b];
-            for (uint32_t o = lane; o < run.y; o += 32) {
-                const uint64_t j = (uint64_t)run.x + o;
-                const uint64_t id = __ldcs(res_id + j);
-                const uint32_t idx = (uint32_t)__ldcs(rec_meta + j);
-                image[idx - (uint32_t)first] = out_value<MODE>(id);
-                if (SECOND && id == ~0ull) ++my_miss;
-            }
+#pragma unroll 4
+        for (uint32_t p = threadIdx.x; p < cnt; p += kBlock) {
+            const uint64_t j = __ldcs(slot_of + first + p);
+            const uint64_t id = __ldcs(res_id + j);
+            const uint32_t idx = (uint32_t)rec_meta[j];
+            image[idx - (uint32_t)first] = out_value<MODE>(id);
+            if (SECOND && id == ~0ull) ++my_miss;
         }
         if (SECOND) {
-            // slots of the tile's misses in the round-2 list: one reservation per tile, warps in order
-            for (int o = 16; o > 0; o >>= 1) my_miss += __shfl_down_sync(0xffffffffu, my_miss, o);
-            if (lane == 0) warp_miss[wid] = my_miss;
-            __syncthreads();
+            // slots of the tile's misses in the round-2 list: one reservation per tile
+            const uint32_t before = cta_exclusive_scan<kBlock>(my_miss, scratch);
+            const uint32_t total = scratch[kBlock / 32];
             if (threadIdx.x == 0) {
-                uint32_t run = 0;
-                for (int w = 0; w < kBlock / 32; ++w) { const uint32_t t = warp_miss[w]; warp_miss[w] = run; run += t; }
-                warp_miss[kBlock / 32] = run;
-                s_seg = run ? (uint32_t)atomicAdd(miss_total, (unsigned long long)run) : 0;
-                seg[tile] = make_uint2(s_seg, run);
+                s_seg = total ? (uint32_t)atomicAdd(miss_total, (unsigned long long)total) : 0;
+                seg[tile] = make_uint2(s_seg, total);
             }
             __syncthreads();
-            if (warp_miss[kBlock / 32]) {                         // CTA-uniform
-                uint32_t slot = s_seg + warp_miss[wid];
-                for (uint32_t b = wid; b < n_bins; b += kBlock / 32) {
-                    const uint2 run = table[(uint64_t)tile * n_bins + b];
-                    for (uint32_t o0 = 0; o0 < run.y; o0 += 32) {
-                        const uint32_t o = o0 + lane;
-                        const uint64_t j = (uint64_t)run.x + o;
-                        const bool miss = o < run.y && res_id[j] == ~0ull;
-                        const uint32_t mask = __ballot_sync(0xffffffffu, miss);
-                        if (miss) {
-                            const uint32_t at = slot + __popc(mask & ((1u << lane) - 1));
-                            const Kmer<W> xr = kmer_rc(load_plain(rec_kmer, j, (Kmer<W>*)nullptr), ix.k);     // src/dictionary.cpp:72
-                            const uint32_t meta = bin_meta_of<W, false>(ix, xr, bin_shift);
-                            store_plain(miss_kmer, at, xr);
-                            miss_idx[at] = (uint32_t)rec_meta[j];
-                            miss_meta1[at] = meta;
-                            atomicAdd(&hist[meta & 0xffffu], 1u);
-                        }
-                        slot += __popc(mask);
-                    }
+            if (total) {                                          // CTA-uniform
+                uint32_t at = s_seg + before;
+                for (uint32_t p = threadIdx.x; p < cnt; p += kBlock) {
+                    const uint64_t j = slot_of[first + p];
+                    if (res_id[j] != ~0ull) continue;
+                    const Kmer<W> xr = kmer_rc(load_plain(rec_kmer, j, (Kmer<W>*)nullptr), ix.k);     // src/dictionary.cpp:72
+                    const uint32_t meta = bin_meta_of<W, false>(ix, xr, bin_shift);
+                    store_plain(miss_kmer, at, xr);
+                    miss_idx[at] = (uint32_t)rec_meta[j];
+                    miss_meta1[at] = meta;
+                    atomicAdd(&hist[meta & 0xffffu], 1u);
+                    ++at;
                 }
             }
         }
@@ -392,25 +379,23 @@ gather_tile_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __res
 // C2: one CTA per tile that had misses: read the ids block back, patch the round-2 results in, store it
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
-patch_tile_kernel(const uint64_t* __restrict__ rec_meta, const uint64_t* __restrict__ res_id, const uint2* __restrict__ table,
-                  const uint2* __restrict__ seg, uint64_t n_queries, uint32_t n_tiles, uint32_t n_bins, void* __restrict__ out) {
+patch_tile_kernel(const uint64_t* __restrict__ rec_meta, const uint64_t* __restrict__ res_id, const uint32_t* __restrict__ slot_of,
+                  const uint2* __restrict__ seg, uint64_t n_queries, uint32_t n_tiles, void* __restrict__ out) {
     using T = typename OutT<MODE>::type;
     extern __shared__ __align__(16) uint8_t smem[];
     T* image = reinterpret_cast<T*>(smem);
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (seg[tile].y == 0) continue;                       // CTA-uniform: nothing of this tile went to round 2
+        const uint2 sg = seg[tile];
+        if (sg.y == 0) continue;                              // CTA-uniform: nothing of this tile went to round 2
         const uint64_t first = (uint64_t)tile * kOutTile;
         const uint32_t cnt = (uint32_t)(n_queries - first < (uint64_t)kOutTile ? n_queries - first : kOutTile);
         T* dst = static_cast<T*>(out) + first;
         for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) image[i] = dst[i];
         __syncthreads();
-        for (uint32_t b = wid; b < n_bins; b += kBlock / 32) {
-            const uint2 run = table[(uint64_t)tile * n_bins + b];
-            for (uint32_t o = lane; o < run.y; o += 32) {
-                const uint64_t j = (uint64_t)run.x + o;
-                image[(uint32_t)__ldcs(rec_meta + j) - (uint32_t)first] = out_value<MODE>(__ldcs(res_id + j));
-            }
+#pragma unroll 4
+        for (uint32_t p = threadIdx.x; p < sg.y; p += kBlock) {
+            const uint64_t j = __ldcs(slot_of + sg.x + p);
+            image[(uint32_t)rec_meta[j] - (uint32_t)first] = out_value<MODE>(__ldcs(res_id + j));
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < cnt; i += kBlock) dst[i] = image[i];
@@ -424,7 +409,7 @@ struct Plan {                      // carve-up of the scratch buffer for a batch
     uint32_t n_ranges, n_bins, n_tiles;
     uint64_t cap;                  // records any array holds
     uint64_t runs;                 // n_ranges * n_bins
-    uint64_t off_meta1, off_rec_kmer, off_rec_meta, off_res, off_miss_kmer, off_miss_idx, off_miss_meta1, off_table, off_seg,
+    uint64_t off_meta1, off_rec_kmer, off_rec_meta, off_res, off_miss_kmer, off_miss_idx, off_miss_meta1, off_slot, off_seg,
         off_ctl[2], ctl_bytes, total;
 };
 
@@ -444,7 +429,7 @@ Plan make_plan(uint32_t kmer_words, uint32_t n_bins, uint64_t n) {
     p.off_miss_kmer = take(p.cap * 8 * kmer_words);
     p.off_miss_idx = take(p.cap * 4);
     p.off_miss_meta1 = take(p.cap * 4);
-    p.off_table = take((uint64_t)p.n_tiles * n_bins * 8);
+    p.off_slot = take(p.cap * 4);
     p.off_seg = take((uint64_t)p.n_tiles * 8);
     // control block: counts, cursor (runs each), bin_start (n_bins + 1), claims (2 x u64)
     p.ctl_bytes = align_up((2 * p.runs + n_bins + 1) * 4, 8) + 16;
@@ -487,7 +472,7 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
     uint64_t* miss_kmer = reinterpret_cast<uint64_t*>(s + p.off_miss_kmer);
     uint32_t* miss_idx = reinterpret_cast<uint32_t*>(s + p.off_miss_idx);
     uint32_t* miss_meta1 = reinterpret_cast<uint32_t*>(s + p.off_miss_meta1);
-    uint2* table = reinterpret_cast<uint2*>(s + p.off_table);
+    uint32_t* slot_of = reinterpret_cast<uint32_t*>(s + p.off_slot);
     uint2* seg = reinterpret_cast<uint2*>(s + p.off_seg);
     const bool canon = ix.canonical != 0, two_rounds = !canon && check_rc;
     const int mode = member ? 2 : (ids32 ? 3 : 0);
@@ -540,9 +525,9 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
         const uint32_t* src_idx = r2 ? miss_idx : nullptr;
         const uint32_t* src_meta1 = r2 ? miss_meta1 : meta1;
         const uint2* src_seg = r2 ? seg : nullptr;
-        const int sgrid = (int)std::min<uint64_t>(nt, (uint64_t)sm * 2);
-        e = w1 ? cfg_launch(bin_scatter_kernel<1>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, table)
-               : cfg_launch(bin_scatter_kernel<2>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, table);
+        const int sgrid = (int)std::min<uint64_t>(nt, (uint64_t)sm * (w1 ? 3 : 2));
+        e = w1 ? cfg_launch(bin_scatter_kernel<1>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, slot_of)
+               : cfg_launch(bin_scatter_kernel<2>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, slot_of);
         if (e != cudaSuccess) return e;
         const int lgrid = sm * 6;
 #define SSHASH_LOOKUP_BINNED(W, CANON) \
@@ -553,7 +538,7 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
         if (e != cudaSuccess) return e;
         if (!r2) {
 #define SSHASH_GATHER(W, MODE, SECOND) \
-            cfg_launch(gather_tile_kernel<W, MODE, SECOND>, tile_grid, kBlock, kOutTile * out_elem + (SECOND ? hist_bytes : 0), ix, (const uint64_t*)rec_kmer, (const uint64_t*)rec_meta, (const uint64_t*)res, (const uint2*)table, n, nt, nb, shift, out, miss_kmer, miss_idx, miss_meta1, seg, c1.counts, c0.claims + 1)
+            cfg_launch(gather_tile_kernel<W, MODE, SECOND>, tile_grid, kBlock, kOutTile * out_elem + (SECOND ? hist_bytes : 0), ix, (const uint64_t*)rec_kmer, (const uint64_t*)rec_meta, (const uint64_t*)res, (const uint32_t*)slot_of, n, nt, nb, shift, out, miss_kmer, miss_idx, miss_meta1, seg, c1.counts, c0.claims + 1)
 #define SSHASH_GATHER_MODE(W, SECOND) (mode == 2 ? SSHASH_GATHER(W, 2, SECOND) : mode == 3 ? SSHASH_GATHER(W, 3, SECOND) : SSHASH_GATHER(W, 0, SECOND))
             if (second) e = w1 ? SSHASH_GATHER_MODE(1, true) : SSHASH_GATHER_MODE(2, true);
             else e = w1 ? SSHASH_GATHER_MODE(1, false) : SSHASH_GATHER_MODE(2, false);
@@ -561,7 +546,7 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
 #undef SSHASH_GATHER
         } else {
 #define SSHASH_PATCH(MODE) \
-            cfg_launch(patch_tile_kernel<MODE>, tile_grid, kBlock, kOutTile * out_elem, (const uint64_t*)rec_meta, (const uint64_t*)res, (const uint2*)table, (const uint2*)seg, n, nt, nb, out)
+            cfg_launch(patch_tile_kernel<MODE>, tile_grid, kBlock, kOutTile * out_elem, (const uint64_t*)rec_meta, (const uint64_t*)res, (const uint32_t*)slot_of, (const uint2*)seg, n, nt, out)
             e = mode == 2 ? SSHASH_PATCH(2) : mode == 3 ? SSHASH_PATCH(3) : SSHASH_PATCH(0);
 #undef SSHASH_PATCH
         }

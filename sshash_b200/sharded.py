@@ -43,7 +43,7 @@ class ShardedLookup:
     """lookup_fn(kmers_chunk) -> ids_chunk runs on this rank's device (Dictionary.lookup_batch)."""
 
     def __init__(self, lookup_fn: Callable, words: int = 1, group=None, chunk_queries: int = 1 << 25,
-                 lookup_into: Optional[Callable] = None, mode: str = "p2p"):
+                 lookup_into: Optional[Callable] = None, mode: str = "p2p", ids_dtype=None):
         import torch.distributed as dist
         self.dist = dist
         self.lookup_fn = lookup_fn
@@ -58,11 +58,15 @@ class ShardedLookup:
         if mode in ("peer", "copy") and lookup_into is None:
             raise ValueError("mode '%s' needs lookup_into" % mode)
         self.mode = mode
+        if ids_dtype is None:
+            import torch
+            ids_dtype = torch.int64
+        self.ids_dtype = ids_dtype           # torch.int64 (reference-width ids) or torch.int32 (sshash_gpu_lookup_batch_u32)
         self._symm = None                    # (buffer, handle, capacity, dst)
         self._side = None                    # copy stream of mode "copy"
 
     @classmethod
-    def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25, mode: str = "auto"):
+    def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25, mode: str = "auto", ids32: bool = False):
         """mode "auto": on NCCL (GPUs of one box) peer stores for 2 ranks, copy engines beyond (rank dst's
         NVLink ingress is the limit there and scattered 8-byte stores use it badly: measured at N=8 on
         a 2.5e9-k-mer index 18.8 ms per 8 x 1.25e8 lookups with "copy", 25.9 with "peer", 26.8 with
@@ -73,6 +77,10 @@ class ShardedLookup:
                 mode = "peer" if dist.get_world_size(group) <= 2 else "copy"
             else:
                 mode = "p2p"
+        import torch
+        if ids32:   # 32-bit ids (dictionaries with < 2^32 - 1 k-mers): half the bytes into rank dst's NVLink ingress
+            return cls(lambda k: dictionary.lookup_batch_u32(k), words=dictionary.words, group=group, chunk_queries=chunk_queries,
+                       lookup_into=lambda k, out: dictionary.lookup_batch_u32(k, out=out), mode=mode, ids_dtype=torch.int32)
         return cls(lambda k: dictionary.lookup_batch(k), words=dictionary.words, group=group,
                    chunk_queries=chunk_queries, lookup_into=lambda k, out: dictionary.lookup_batch(k, out=out), mode=mode)
 
@@ -82,11 +90,11 @@ class ShardedLookup:
         import torch.distributed._symmetric_memory as symm_mem
         if self._symm is None or self._symm[2] < total or self._symm[3] != dst:
             cap = int(total)
-            buf = symm_mem.empty(cap, dtype=torch.int64, device=device)
+            buf = symm_mem.empty(cap, dtype=self.ids_dtype, device=device)
             hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
             self._symm = (buf, hdl, cap, dst)
         buf, hdl, cap, _ = self._symm
-        return buf, hdl, hdl.get_buffer(dst, (cap,), torch.int64)
+        return buf, hdl, hdl.get_buffer(dst, (cap,), self.ids_dtype)
 
     def _lookup_peer(self, local_kmers, dst: int, sizes, starts):
         n_local = sizes[self.rank]
@@ -112,7 +120,7 @@ class ShardedLookup:
                 self.lookup_into(local_kmers, mine)
             local_ids = mine
         else:
-            local_ids = torch.empty(n_local, dtype=torch.int64, device=local_kmers.device)
+            local_ids = torch.empty(n_local, dtype=self.ids_dtype, device=local_kmers.device)
             if self._side is None:
                 self._side = torch.cuda.Stream(device=local_kmers.device)
             main = torch.cuda.current_stream(local_kmers.device)
@@ -138,7 +146,7 @@ class ShardedLookup:
         dist = self.dist
         n_local = local_kmers.numel() // self.words
         if dst is None or self.world == 1 or self.mode == "p2p":
-            local_ids = torch.empty(n_local, dtype=torch.int64, device=local_kmers.device)
+            local_ids = torch.empty(n_local, dtype=self.ids_dtype, device=local_kmers.device)
         if dst is None or self.world == 1:
             for lo in range(0, n_local, self.chunk):
                 hi = min(n_local, lo + self.chunk)
@@ -157,7 +165,7 @@ class ShardedLookup:
         gathered = None
         pending = []
         if self.rank == dst:
-            gathered = torch.empty(sum(sizes), dtype=torch.int64, device=local_kmers.device)
+            gathered = torch.empty(sum(sizes), dtype=self.ids_dtype, device=local_kmers.device)
             # post the receives for every remote chunk up front; they complete as the senders progress
             for r in range(self.world):
                 if r == dst:

@@ -13,7 +13,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def test_reference_arm_prints_one_contract_line():
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--queries", "2000000"],
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
@@ -24,10 +24,12 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 1e5 and "workload" in d["config"]
+    import bench
+    assert d["config"] == bench.make_config(2000000, 1)      # the two arms print the same config
 
 
 def test_committed_b200_line_has_every_contract_key():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_v*.json")), key=os.path.getmtime)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9]_bench_v*.json")), key=os.path.getmtime)
     line = [l for l in open(files[-1]) if l.startswith("{")][-1]
     d = json.loads(line)
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d), sorted(set(d))
