@@ -38,7 +38,33 @@ int main(int argc, char** argv) {
         bool back_ok = false;
         for (auto const& b : nb.backward) back_ok |= b.kmer_id == 0;
         std::printf("kmer_neighbours(access(1)): backward contains id 0: %s\n", back_ok ? "yes" : "no");
-        return bad == 0 && r.kmer_id == 0 && back_ok ? 0 : 1;
+        // the stateful per-k-mer object (include/streaming_query.hpp:36-115): 10 consecutive k-mers of string 0
+        // walked forward = 1 search + 9 extensions, then an invalid k-mer, then a k-mer of another string = a search
+        sshash_b200::streaming_query sq(&dict);
+        uint64_t sq_bad = 0;
+        for (uint64_t id = 0; id != 10; ++id) {
+            dict.access(id, kmer.data());
+            sq_bad += sq.lookup(kmer.c_str()).kmer_id != id;
+        }
+        std::string inval(dict.k(), 'N');
+        sq_bad += sq.lookup(inval.c_str()).kmer_id != sshash_b200::constants::invalid_uint64;
+        dict.access(dict.num_kmers() - 1, kmer.data());
+        sq_bad += sq.lookup(kmer.c_str()).kmer_id != dict.num_kmers() - 1;
+        sq_bad += !(sq.num_searches() == 2 && sq.num_extensions() == 9 && sq.num_invalid_lookups() == 1 && sq.num_negative_lookups() == 0);
+        std::printf("streaming_query object: %lu searches, %lu extensions, %lu invalid -> %s\n", sq.num_searches(), sq.num_extensions(),
+                    sq.num_invalid_lookups(), sq_bad ? "MISMATCH" : "ok");
+        // every GPU of the box behind one handle: same ids, 32-bit ids, membership
+        sshash_b200::multi_dictionary multi(argv[1]);
+        std::vector<uint64_t> got_m(n);
+        std::vector<uint32_t> got32(n);
+        std::vector<uint8_t> mem(n);
+        multi.lookup_batch(kmers.data(), n, got_m.data());
+        multi.lookup_batch_u32(kmers.data(), n, got32.data());
+        multi.is_member_batch(kmers.data(), n, mem.data());
+        uint64_t multi_bad = 0;
+        for (uint64_t i = 0; i != n; ++i) multi_bad += (got_m[i] != ids[i]) + (got32[i] != (uint32_t)ids[i]) + (mem[i] != 1);
+        std::printf("multi_dictionary over %d GPU(s): %lu mismatches\n", multi.num_devices(), multi_bad);
+        return bad == 0 && r.kmer_id == 0 && back_ok && sq_bad == 0 && multi_bad == 0 ? 0 : 1;
     } catch (std::exception const& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -94,8 +94,9 @@ struct Workspace {
     } sslots[2];
     cudaStream_t copy_stream = nullptr;
     // file driver with device-side record parsing
-    uint8_t* d_raw = nullptr; uint64_t raw_cap = 0;
-    uint64_t* d_tiles = nullptr; uint64_t tiles_cap = 0;
+    uint8_t* d_raw[2] = {nullptr, nullptr}; uint64_t raw_cap[2] = {0, 0};          // two chunks in flight: chunk c+1 is copied
+    uint64_t* d_tiles[2] = {nullptr, nullptr}; uint64_t tiles_cap[2] = {0, 0};    // and line-counted while chunk c is streamed
+    cudaEvent_t file_counted[2] = {nullptr, nullptr}, file_done[2] = {nullptr, nullptr};
     uint64_t* d_line_start = nullptr; uint64_t ls_cap = 0;
     uint64_t* d_spans = nullptr; uint64_t spans_cap = 0;
     uint8_t* h_file[2] = {nullptr, nullptr}; uint64_t h_file_cap = 0;   // pinned
@@ -112,7 +113,12 @@ struct Workspace {
         cudaFree(d_win_offsets); cudaFree(d_block_sums);
         cudaFree(d_win_id); cudaFree(d_win_aux); cudaFree(d_ids); cudaFree(d_counters); cudaFree(d_anchors);
         if (h_counters) cudaFreeHost(h_counters);
-        cudaFree(d_raw); cudaFree(d_tiles); cudaFree(d_line_start); cudaFree(d_spans); cudaFree(d_bin);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(d_raw[i]); cudaFree(d_tiles[i]);
+            if (file_counted[i]) cudaEventDestroy(file_counted[i]);
+            if (file_done[i]) cudaEventDestroy(file_done[i]);
+        }
+        cudaFree(d_line_start); cudaFree(d_spans); cudaFree(d_bin);
         for (auto& ss : sslots) {
             cudaFree(ss.d_bases); cudaFree(ss.d_ro); cudaFree(ss.d_ids);
             if (ss.ready) cudaEventDestroy(ss.ready);
@@ -1136,8 +1142,17 @@ int stream_file_device_parse(const sshash_gpu_dict* dict, const char* filename, 
         CU(cudaMalloc(reinterpret_cast<void**>(&w.d_counters), 8 * sizeof(unsigned long long)));
         CU(cudaMallocHost(reinterpret_cast<void**>(&w.h_counters), 8 * sizeof(unsigned long long)));
     }
+    // Two streams: the copy stream moves chunk c+1 to HBM and counts its lines (the one number the host needs)
+    // while the compute stream runs the span + streaming kernels of chunk c.
     cudaStream_t s = dict->stream;
+    if (!w.copy_stream) CU(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = w.copy_stream;
+    for (int i = 0; i < 2; ++i) {
+        if (!w.file_counted[i]) CU(cudaEventCreateWithFlags(&w.file_counted[i], cudaEventDisableTiming));
+        if (!w.file_done[i]) CU(cudaEventCreateWithFlags(&w.file_done[i], cudaEventDisableTiming));
+    }
     CU(cudaMemsetAsync(w.d_counters, 0, 8 * sizeof(unsigned long long), s));
+    bool slot_used[2] = {false, false};
 
     // reader thread: fills slot 0, 1, 0, ... at offset carry_max, hands each over with its byte count
     struct Handoff {
@@ -1185,13 +1200,17 @@ int stream_file_device_parse(const sshash_gpu_dict* dict, const char* filename, 
             n += stride + 1;
         }
         const uint64_t tiles = parse_tiles(n);
-        CU(ensure(w.d_raw, w.raw_cap, n + 64));
-        CU(ensure(w.d_tiles, w.tiles_cap, (tiles + 2) * 8));
-        CU(cudaMemcpyAsync(w.d_raw, begin, n, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(w.d_tiles + tiles, 0, 8, s));
-        CU(launch_count_lines(w.d_raw, n, w.d_tiles, s));
-        CU(cudaMemcpyAsync(w.h_counters + 6, w.d_tiles + tiles, 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        if (slot_used[slot]) CU(cudaEventSynchronize(w.file_done[slot]));   // chunk c-2 has been streamed: its buffers are free (ensure may reallocate)
+        CU(ensure(w.d_raw[slot], w.raw_cap[slot], n + 64));
+        CU(ensure(w.d_tiles[slot], w.tiles_cap[slot], (tiles + 2) * 8));
+        uint8_t* d_raw = w.d_raw[slot];
+        uint64_t* d_tiles = w.d_tiles[slot];
+        CU(cudaMemcpyAsync(d_raw, begin, n, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemsetAsync(d_tiles + tiles, 0, 8, cs));
+        CU(launch_count_lines(d_raw, n, d_tiles, cs));
+        CU(cudaMemcpyAsync(w.h_counters + 6, d_tiles + tiles, 8, cudaMemcpyDeviceToHost, cs));
+        CU(cudaEventRecord(w.file_counted[slot], cs));
+        CU(cudaStreamSynchronize(cs));                   // waits for this chunk's copy + count only; chunk c-1 keeps streaming
         const uint64_t lines = w.h_counters[6], records = lines / stride;
         if (records == 0 && !eof) { *need_host_parser = true; return SSHASH_GPU_OK; }
         // the unfinished record: everything after the newline that ends line stride * records - 1
@@ -1212,14 +1231,17 @@ int stream_file_device_parse(const sshash_gpu_dict* dict, const char* filename, 
         }
         ho.cv.notify_all();
         if (records) {
-            CU(ensure(w.d_line_start, w.ls_cap, (lines + 2) * 8));
+            CU(cudaStreamWaitEvent(s, w.file_counted[slot], 0));
+            CU(ensure(w.d_line_start, w.ls_cap, (lines + 2) * 8));   // (grows only while the compute stream is idle or after a sync below)
             CU(ensure(w.d_spans, w.spans_cap, 2 * records * 8));
-            CU(launch_read_spans(w.d_raw, n, w.d_tiles, w.d_line_start, records, stride, w.d_spans, w.d_spans + records,
+            CU(launch_read_spans(d_raw, n, d_tiles, w.d_line_start, records, stride, w.d_spans, w.d_spans + records,
                                  dict->ctx.sm_count, s));
-            st = streaming_device(dict, w, reinterpret_cast<const char*>(w.d_raw), w.d_spans, w.d_spans + records, records, n + 1,
+            st = streaming_device(dict, w, reinterpret_cast<const char*>(d_raw), w.d_spans, w.d_spans + records, records, n + 1,
                                   nullptr, s);
             if (st) return st;
         }
+        CU(cudaEventRecord(w.file_done[slot], s));
+        slot_used[slot] = true;
         if (eof) break;
     }
     CU(cudaMemcpyAsync(w.h_counters, w.d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

@@ -164,7 +164,7 @@ __device__ __forceinline__ Kmer<2> load_plain(const uint64_t* in, uint64_t i, Km
 // slot_of[first + p] = slot, in the bin-major record arrays, of the p-th record of the tile in bin order: the
 // way back for C (consecutive p of one bin are consecutive slots).
 template <int W>
-__global__ void __launch_bounds__(kSortThreads, W == 1 ? 3 : 2)
+__global__ void __launch_bounds__(kSortThreads, 2)
 bin_scatter_kernel(const uint64_t* __restrict__ kmers, const uint32_t* __restrict__ src_idx, const uint2* __restrict__ seg,
                    uint64_t n_queries, uint32_t n_tiles, uint32_t n_bins, const uint32_t* __restrict__ meta1,
                    uint32_t* __restrict__ cursor, uint64_t* __restrict__ rec_kmer, uint64_t* __restrict__ rec_meta,
@@ -340,8 +340,12 @@ gather_tile_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __res
             if (SECOND && id == ~0ull) ++my_miss;
         }
         if (SECOND) {
-            // slots of the tile's misses in the round-2 list: one reservation per tile
-            const uint32_t before = cta_exclusive_scan<kBlock>(my_miss, scratch);
+            // slots of the tile's misses in the round-2 list: one reservation per tile, one sub-range per warp,
+            // filled in ballot order so that a warp's stores are adjacent
+            const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            uint32_t warp_total = my_miss;
+            for (int o = 16; o > 0; o >>= 1) warp_total += __shfl_xor_sync(0xffffffffu, warp_total, o);
+            const uint32_t warp_before = cta_exclusive_scan<kBlock>(lane == 0 ? warp_total : 0u, scratch);   // valid in lane 0
             const uint32_t total = scratch[kBlock / 32];
             if (threadIdx.x == 0) {
                 s_seg = total ? (uint32_t)atomicAdd(miss_total, (unsigned long long)total) : 0;
@@ -349,17 +353,23 @@ gather_tile_kernel(const __grid_constant__ DeviceIndex ix, const uint64_t* __res
             }
             __syncthreads();
             if (total) {                                          // CTA-uniform
-                uint32_t at = s_seg + before;
-                for (uint32_t p = threadIdx.x; p < cnt; p += kBlock) {
-                    const uint64_t j = slot_of[first + p];
-                    if (res_id[j] != ~0ull) continue;
-                    const Kmer<W> xr = kmer_rc(load_plain(rec_kmer, j, (Kmer<W>*)nullptr), ix.k);     // src/dictionary.cpp:72
-                    const uint32_t meta = bin_meta_of<W, false>(ix, xr, bin_shift);
-                    store_plain(miss_kmer, at, xr);
-                    miss_idx[at] = (uint32_t)rec_meta[j];
-                    miss_meta1[at] = meta;
-                    atomicAdd(&hist[meta & 0xffffu], 1u);
-                    ++at;
+                uint32_t at = s_seg + __shfl_sync(0xffffffffu, warp_before, 0);
+                for (uint32_t p0 = wid * 32; p0 < cnt; p0 += kBlock) {     // warp-uniform trip count
+                    const uint32_t p = p0 + lane;
+                    uint64_t j = 0;
+                    bool miss = false;
+                    if (p < cnt) { j = slot_of[first + p]; miss = res_id[j] == ~0ull; }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, miss);
+                    if (miss) {
+                        const uint32_t slot = at + __popc(mask & ((1u << lane) - 1));
+                        const Kmer<W> xr = kmer_rc(load_plain(rec_kmer, j, (Kmer<W>*)nullptr), ix.k);     // src/dictionary.cpp:72
+                        const uint32_t meta = bin_meta_of<W, false>(ix, xr, bin_shift);
+                        store_plain(miss_kmer, slot, xr);
+                        miss_idx[slot] = (uint32_t)rec_meta[j];
+                        miss_meta1[slot] = meta;
+                        atomicAdd(&hist[meta & 0xffffu], 1u);
+                    }
+                    at += __popc(mask);
                 }
             }
         }
@@ -525,7 +535,7 @@ cudaError_t launch_lookup_binned(const DeviceIndex& ix, const LaunchCtx& ctx, co
         const uint32_t* src_idx = r2 ? miss_idx : nullptr;
         const uint32_t* src_meta1 = r2 ? miss_meta1 : meta1;
         const uint2* src_seg = r2 ? seg : nullptr;
-        const int sgrid = (int)std::min<uint64_t>(nt, (uint64_t)sm * (w1 ? 3 : 2));
+        const int sgrid = (int)std::min<uint64_t>(nt, (uint64_t)sm * 2);
         e = w1 ? cfg_launch(bin_scatter_kernel<1>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, slot_of)
                : cfg_launch(bin_scatter_kernel<2>, sgrid, kSortThreads, sort_smem, src_kmer, src_idx, src_seg, n, nt, nb, src_meta1, c.cursor, rec_kmer, rec_meta, slot_of);
         if (e != cudaSuccess) return e;

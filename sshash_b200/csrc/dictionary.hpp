@@ -119,6 +119,11 @@ public:
                       lookup_result* full = nullptr, void* stream = nullptr) const {
         check(sshash_gpu_lookup_batch_ascii(m_dict, string_kmers, n, check_reverse_complement, kmer_ids, full, stream));
     }
+    /* 32-bit ids (dictionaries with < 2^32 - 1 k-mers): "not found" is UINT32_MAX */
+    void lookup_batch_u32(uint64_t const* kmers, uint64_t n, uint32_t* kmer_ids32, bool check_reverse_complement = true,
+                          void* stream = nullptr) const {
+        check(sshash_gpu_lookup_batch_u32(m_dict, kmers, n, check_reverse_complement, kmer_ids32, stream));
+    }
     void is_member_batch(uint64_t const* kmers, uint64_t n, uint8_t* member, bool check_reverse_complement = true,
                          void* stream = nullptr) const {
         check(sshash_gpu_is_member_batch(m_dict, kmers, n, check_reverse_complement, member, stream));
@@ -182,6 +187,99 @@ private:
     sshash_gpu_dict* m_dict = nullptr;
     sshash_gpu_info_t m_info{};
     uint64_t m_words = 1;
+};
+
+// The same index replicated on several GPUs of one box behind ONE handle (sshash_gpu_multi_*): batches are
+// sharded by query inside the library, results come back in query order.  devices empty = every GPU.
+class multi_dictionary {
+public:
+    explicit multi_dictionary(std::string const& index_filename, std::vector<int> const& devices = {}, int max_k = 0) {
+        check(sshash_gpu_multi_open(index_filename.c_str(), devices.empty() ? nullptr : devices.data(), (int)devices.size(), max_k, &m_multi));
+        check(sshash_gpu_info(sshash_gpu_multi_dict(m_multi, 0), &m_info));
+    }
+    ~multi_dictionary() { sshash_gpu_multi_close(m_multi); }
+    multi_dictionary(multi_dictionary const&) = delete;
+    multi_dictionary& operator=(multi_dictionary const&) = delete;
+
+    int num_devices() const { return sshash_gpu_multi_num_devices(m_multi); }
+    uint64_t num_kmers() const { return m_info.num_kmers; }
+    uint64_t k() const { return m_info.k; }
+    uint64_t words_per_kmer() const { return m_info.max_k == 31 ? 1 : 2; }
+    sshash_gpu_dict const* replica(int i) const { return sshash_gpu_multi_dict(m_multi, i); }
+
+    void lookup_batch(uint64_t const* kmers, uint64_t n, uint64_t* kmer_ids, bool check_reverse_complement = true) const {
+        check(sshash_gpu_multi_lookup_batch(m_multi, kmers, n, check_reverse_complement, kmer_ids));
+    }
+    void lookup_batch_u32(uint64_t const* kmers, uint64_t n, uint32_t* kmer_ids32, bool check_reverse_complement = true) const {
+        check(sshash_gpu_multi_lookup_batch_u32(m_multi, kmers, n, check_reverse_complement, kmer_ids32));
+    }
+    void is_member_batch(uint64_t const* kmers, uint64_t n, uint8_t* member, bool check_reverse_complement = true) const {
+        check(sshash_gpu_multi_is_member_batch(m_multi, kmers, n, check_reverse_complement, member));
+    }
+    streaming_query_report streaming_query(char const* bases, uint64_t const* read_offsets, uint64_t num_reads,
+                                           uint64_t* kmer_ids = nullptr) const {
+        streaming_query_report r;
+        check(sshash_gpu_multi_streaming_batch(m_multi, bases, read_offsets, num_reads, kmer_ids, &r));
+        return r;
+    }
+
+private:
+    static void check(int status) {
+        if (status != SSHASH_GPU_OK) throw std::runtime_error(sshash_gpu_last_error());
+    }
+    sshash_gpu_multi* m_multi = nullptr;
+    sshash_gpu_info_t m_info{};
+};
+
+// Stateful per-k-mer streaming object with the reference's interface (include/streaming_query.hpp:36-115):
+// reset(), lookup(kmer) one k-mer at a time, the four counters.  For callers that interleave their own
+// logic with lookups; every call is a one-element batch (tens of microseconds) -- whole reads belong in
+// dictionary::streaming_query / streaming_query_from_file.  The record returned is dictionary::lookup's
+// (the reference asserts they are equal, :107); a lookup counts as an EXTENSION when the previous one
+// was positive and this k-mer is the next one of the same string in the previous orientation
+// (:88-99, :189-195), else as a search -- exact on indexes that keep SSHash's distinct-k-mer contract.
+class streaming_query {
+public:
+    explicit streaming_query(dictionary const* dict) : m_dict(dict) { reset(); }
+    void reset() { m_prev.kmer_id = constants::invalid_uint64; }
+    lookup_result lookup(char const* kmer) {
+        ++m_num_kmers;
+        for (uint64_t i = 0; i != m_dict->k(); ++i) {        // kmer.hpp:209-219: only ACGTacgt are valid
+            const char c = kmer[i] & 0xDF;
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+                ++m_num_invalid;
+                reset();
+                lookup_result r{};
+                r.kmer_id = r.kmer_id_in_string = r.kmer_offset = r.string_id = r.string_begin = r.string_end = constants::invalid_uint64;
+                r.kmer_orientation = constants::forward_orientation;
+                return r;
+            }
+        }
+        lookup_result r = m_dict->lookup(kmer, true);
+        if (r.kmer_id == constants::invalid_uint64) { ++m_num_negative; reset(); return r; }
+        bool extension = false;
+        if (m_prev.kmer_id != constants::invalid_uint64 && m_prev.string_id == r.string_id) {
+            const uint64_t last = m_prev.string_end - m_prev.string_begin - m_dict->k();   // id_in_string of the string's last k-mer
+            if (m_prev.kmer_orientation > 0) extension = m_prev.kmer_id_in_string != last && r.kmer_id == m_prev.kmer_id + 1;
+            else extension = m_prev.kmer_id_in_string != 0 && r.kmer_id + 1 == m_prev.kmer_id;
+        }
+        if (extension) ++m_num_extensions; else ++m_num_searches;
+        m_prev = r;
+        return r;
+    }
+    uint64_t num_searches() const { return m_num_searches; }
+    uint64_t num_extensions() const { return m_num_extensions; }
+    uint64_t num_positive_lookups() const { return m_num_searches + m_num_extensions; }
+    uint64_t num_negative_lookups() const { return m_num_negative; }
+    uint64_t num_invalid_lookups() const { return m_num_invalid; }
+    streaming_query_report report() const {
+        return {m_num_kmers, m_num_searches + m_num_extensions, m_num_negative, m_num_invalid, m_num_searches, m_num_extensions};
+    }
+
+private:
+    dictionary const* m_dict;
+    lookup_result m_prev{};
+    uint64_t m_num_kmers = 0, m_num_searches = 0, m_num_extensions = 0, m_num_negative = 0, m_num_invalid = 0;
 };
 
 }  // namespace sshash_b200

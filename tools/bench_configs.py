@@ -82,8 +82,10 @@ def lookup_config(name, idx, k, b_alg_fwd, b_alg_mix, queries=100_000_000, cpu_s
     if ref.available(max_k):
         rd = ref.RefDictionary(idx, max_k=max_k)
         sample = mix[: cpu_sample].cpu().numpy().view(np.uint64).reshape(-1)
-        got = rd.lookup(sample[: 100000 * d.words])
-        assert (got.view(np.int64) == ids[:100000].cpu().numpy()).all()
+        chk = min(1_000_000, cpu_sample)          # GPU ids == the reference CPU dictionary's ids on the first 1e6 queries
+        got = rd.lookup(sample[: chk * d.words], threads=threads())
+        assert (got.view(np.int64) == ids[:chk].cpu().numpy()).all()
+        res["checked_vs_reference"] = chk
         t = threads()
         secs = rd.time_lookup(sample, threads=t)
         one = rd.time_lookup(sample[: (cpu_sample // 8) * d.words], threads=1)
@@ -160,6 +162,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="cfg2,t5e8,t5e8_canonical,k63,stream,stream_t5e8,human")
     ap.add_argument("--workdir", default=None)
+    ap.add_argument("--keep", action="store_true", help="keep the synthetic indexes (for a following ncu pass)")
     a = ap.parse_args()
     wd = a.workdir or tempfile.mkdtemp(prefix="sshash_cfg_")
     os.makedirs(wd, exist_ok=True)
@@ -181,6 +184,13 @@ def main():
             r = lookup_config("cfg4 (scaled): synthetic 5e8 k-mers k63 m25", idx, 63, 248.0, 296.0)
             r["build_s"] = bs
             os.remove(idx)
+        elif c == "k63_3e9":
+            # BASELINE configs[3] at its stated scale: k=63 m=25 (script/build.py:28-30), ~3e9 k-mers, HBM-resident
+            idx, bs = build_index(wd, 3000000, 1062, 63, 25)
+            r = lookup_config("cfg4: synthetic 3e9 k-mers k63 m25 (3e6 strings x 1062 bases), HBM-resident", idx, 63, 248.0, 296.0)
+            r["build_s"] = bs
+            if not a.keep:
+                os.remove(idx)
         elif c == "k63_canonical":
             idx, bs = build_index(wd, 500000, 1062, 63, 25, canonical=True)
             r = lookup_config("synthetic 5e8 k-mers k63 m25 canonical", idx, 63, 248.0, 248.0)
@@ -190,7 +200,8 @@ def main():
             idx, bs = build_index(wd, 2500000, 1030, 31, 21)
             r = lookup_config("cfg5 index: synthetic human-scale 2.5e9 k-mers k31 m21", idx, 31, 208.0, 256.0)
             r["build_s"] = bs
-            os.remove(idx)
+            if not a.keep:
+                os.remove(idx)
         elif c == "stream":
             r = stream_config("cfg3 on the cfg-1 index: 1e7 synthetic 150-bp reads, 50 % hit", BUNDLED, 31)
         elif c == "stream_t5e8":
