@@ -298,6 +298,14 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def widen_ids(t):
+    """ids as int64 bit patterns: 32-bit ids (int32 tensors, UINT32_MAX = not found) are zero-extended, not found -> -1"""
+    import torch
+    if t.dtype == torch.int64:
+        return t
+    return torch.where(t == -1, torch.full((), -1, dtype=torch.int64, device=t.device), t.to(torch.int64) & 0xFFFFFFFF)
+
+
 def time_e2e(fn, steps: int, barrier, dev, world: int):
     """wall time of `steps` calls of a host-buffer entry point, max over ranks"""
     import torch
@@ -412,7 +420,7 @@ def main():
             if rank != 0:
                 return
             for r in range(world):
-                sl = gathered[r * n:(r + 1) * n].to(torch.int64)
+                sl = widen_ids(gathered[r * n:(r + 1) * n])
                 got = torch.stack([sl.sum(), (sl * w_local).sum()])
                 assert torch.equal(got, sums[r]), "gathered ids of rank %d are wrong (%s)" % (r, what)
 
@@ -431,7 +439,7 @@ def main():
                 g_ms, _ = timed(step_gather, args.steps)
                 g_launches = sshash_b200.launch_count() - l0
                 local_ids, gathered = state["r"]
-                assert torch.equal(local_ids.to(torch.int64), ids), "local ids differ from the sampled ids"
+                assert torch.equal(widen_ids(local_ids), ids), "local ids differ from the sampled ids"
                 verify(gathered, "%s ids, mode %s" % ("u32" if ids32 else "u64", mode))
                 key = ("u32_" if ids32 else "u64_") + mode
                 bytes_in = (world - 1) * n * (4 if ids32 else 8)
@@ -460,7 +468,7 @@ def main():
     h32 = torch.empty(n, dtype=torch.int32, pin_memory=True)
     h32_np = h32.numpy().view(np.uint32)
     s32 = time_e2e(lambda: d.lookup_batch_u32(h_in_np, out=h32_np), max(2, args.steps // 2), barrier, dev, world)
-    assert torch.equal(h32.to(torch.int64), ids.cpu()), "e2e u32 ids differ from the sampled ids"
+    assert torch.equal(widen_ids(h32), ids.cpu()), "e2e u32 ids differ from the sampled ids"
     e2e["u32_ids"] = {"value": world * n * max(2, args.steps // 2) / s32, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 4}
     smem_ = time_e2e(lambda: d.is_member_batch(h_in_np), max(2, args.steps // 2), barrier, dev, world)
     e2e["is_member"] = {"value": world * n * max(2, args.steps // 2) / smem_, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n}

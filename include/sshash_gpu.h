@@ -118,6 +118,13 @@ SSHASH_GPU_API int sshash_gpu_open(const char* index_path, int device, int max_k
 SSHASH_GPU_API int sshash_gpu_close(sshash_gpu_dict* dict);
 SSHASH_GPU_API int sshash_gpu_info(const sshash_gpu_dict* dict, sshash_gpu_info_t* out);
 
+/* How lookup / membership / access / weight treat a device pointer that lives on ANOTHER GPU.
+   0 (default): staged chunk by chunk with copy-engine transfers, like a host buffer.  1: used in place --
+   the kernels load / store it directly over NVLink; the caller guarantees that it is dereferenceable
+   from the dictionary's GPU (peer access enabled, or a peer-mapped symmetric / IPC allocation).  This
+   is how a per-GPU process delivers its ids straight into another rank's result vector. */
+SSHASH_GPU_API int sshash_gpu_set_peer_inplace(sshash_gpu_dict* dict, int inplace);
+
 /*
  * Batched dictionary::lookup(Kmer uint_kmer, bool check_reverse_complement)
  * (include/dictionary.hpp:42, src/dictionary.cpp:64-78).  kmers: n packed k-mers.

@@ -53,6 +53,7 @@ SYMBOLS = {
     "sshash_gpu_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sshash_gpu_close": (C.c_int, [C.c_void_p]),
     "sshash_gpu_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "sshash_gpu_set_peer_inplace": (C.c_int, [C.c_void_p, C.c_int]),
     "sshash_gpu_lookup_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sshash_gpu_lookup_batch_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]),
     "sshash_gpu_lookup_batch_ascii": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

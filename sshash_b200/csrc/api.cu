@@ -9,6 +9,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -177,6 +178,7 @@ struct sshash_gpu_dict {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     std::vector<std::unique_ptr<Workspace>> pool;
+    std::atomic<int> peer_inplace{0};   // 1: device pointers of OTHER GPUs are dereferenced by the kernels (peer access / symmetric memory)
     std::mutex contract_mu;
     int breaks_contract = -1;   // -1 not checked yet; 1 = duplicated k-mers / rc twins: streaming replays the state machine
 
@@ -528,9 +530,11 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
         void* d_regions = up.raw(regions.data(), regions.size() * sizeof(BinRegion));
         if (!d_regions) return fail(SSHASH_GPU_ECUDA, up.error);
         bp.regions = static_cast<const BinRegion*>(d_regions);
-        // Size rule (measured, profiles/r2_binned_ab.jsonl): the path pays when pilots + codewords are far
-        // beyond L2; SSHASH_GPU_BINNED=0/1 forces, SSHASH_GPU_BINNED_MIN sets the smallest batch that takes it
-        bp.enabled = pilot_bytes_total + cw_total > (256ull << 20) && P >= 4;
+        // Off by default: measured on 5e8-, 2.5e9- and 3e9-k-mer indexes (profiles/r2_binned_ab_v4.jsonl)
+        // the exact reordering around the bin-ordered lookups costs more than the L2 hits save.
+        // SSHASH_GPU_BINNED=1 turns it on, SSHASH_GPU_BINNED_MIN sets the smallest batch that takes it.
+        (void)pilot_bytes_total;
+        bp.enabled = false;
         if (const char* be = std::getenv("SSHASH_GPU_BINNED")) bp.enabled = be[0] == '1';
         bp.min_queries = env_bytes("SSHASH_GPU_BINNED_MIN", 1ull << 22);
         if (const char* pe = std::getenv("SSHASH_GPU_BIN_PREFETCH")) bp.prefetch = pe[0] != '0';
@@ -613,7 +617,9 @@ template <typename Launch>
 int run_batched(const sshash_gpu_dict* d, const void* in, uint64_t in_elem, void* out, uint64_t out_elem, uint64_t n,
                 void* user_stream, Launch launch) {
     if (n == 0) return SSHASH_GPU_OK;
-    const bool in_dev = is_local_device_pointer(in, d->device), out_dev = is_local_device_pointer(out, d->device);
+    const bool any_dev = d->peer_inplace.load(std::memory_order_relaxed) != 0;
+    const bool in_dev = any_dev ? is_device_pointer(in) : is_local_device_pointer(in, d->device);
+    const bool out_dev = any_dev ? is_device_pointer(out) : is_local_device_pointer(out, d->device);
     if (in_dev && out_dev) {
         cudaStream_t s = static_cast<cudaStream_t>(user_stream);   // NULL = the legacy default stream
         CU(launch(in, out, n, s));
@@ -696,6 +702,12 @@ SSHASH_ENTRY(sshash_gpu_open, (const char* index_path, int device, int max_k, ss
 
 SSHASH_ENTRY(sshash_gpu_close, (sshash_gpu_dict* dict), (dict)) {
     delete dict;
+    return SSHASH_GPU_OK;
+}
+
+SSHASH_ENTRY(sshash_gpu_set_peer_inplace, (sshash_gpu_dict* dict, int inplace), (dict, inplace)) {
+    if (!dict) return fail(SSHASH_GPU_EINVAL, "null dictionary handle");
+    dict->peer_inplace.store(inplace ? 1 : 0);
     return SSHASH_GPU_OK;
 }
 
@@ -1084,7 +1096,7 @@ public:
         }
         // plain file: the page-cache copy is the bottleneck of one thread, so slices are read in parallel
         const unsigned hw = std::thread::hardware_concurrency();
-        const uint64_t nt = n >= (4u << 20) ? std::max(1u, std::min(8u, hw ? hw : 1u)) : 1;
+        const uint64_t nt = n >= (4u << 20) ? std::max(1u, std::min(16u, hw ? hw : 1u)) : 1;
         const uint64_t slice = (n + nt - 1) / nt;
         std::vector<int64_t> got(nt, 0);
         auto work = [&](uint64_t t) {

@@ -92,6 +92,11 @@ class Dictionary:
     def __exit__(self, *a):
         self.close()
 
+    def set_peer_inplace(self, inplace: bool) -> None:
+        """Device pointers of OTHER GPUs: staged with copy engines (False, default) or dereferenced by the
+        kernels over NVLink (True; the caller guarantees peer access / a peer-mapped allocation)."""
+        check(self._lib.sshash_gpu_set_peer_inplace(self._h, int(inplace)))
+
     # ---- accessors, include/dictionary.hpp:31-38 ----------------------------------------------
     def k(self) -> int: return self.info["k"]
     def m(self) -> int: return self.info["m"]

@@ -78,6 +78,8 @@ class ShardedLookup:
             else:
                 mode = "p2p"
         import torch
+        if hasattr(dictionary, "set_peer_inplace"):   # "peer": the lookup kernels store straight into rank dst's peer-mapped vector
+            dictionary.set_peer_inplace(mode == "peer")
         if ids32:   # 32-bit ids (dictionaries with < 2^32 - 1 k-mers): half the bytes into rank dst's NVLink ingress
             return cls(lambda k: dictionary.lookup_batch_u32(k), words=dictionary.words, group=group, chunk_queries=chunk_queries,
                        lookup_into=lambda k, out: dictionary.lookup_batch_u32(k, out=out), mode=mode, ids_dtype=torch.int32)

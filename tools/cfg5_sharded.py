@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 25, help="p2p mode: queries per lookup launch / per send of the gather")
     ap.add_argument("--mode", default="auto", choices=["auto", "peer", "copy", "p2p"],
                     help="gather: ids stored straight into rank 0's vector over NVLink (peer) or NCCL send/recv (p2p)")
+    ap.add_argument("--ids32", action="store_true", help="gather 32-bit ids (sshash_gpu_lookup_batch_u32): half the bytes into rank 0")
     a = ap.parse_args()
 
     import torch
@@ -87,7 +88,7 @@ def main():
 
     n_batches = max(1, a.queries_per_rank // a.batch)
     B = a.batch
-    sl = ShardedLookup.for_dictionary(d, chunk_queries=a.chunk, mode=a.mode) if world > 1 else None
+    sl = ShardedLookup.for_dictionary(d, chunk_queries=a.chunk, mode=a.mode, ids32=a.ids32) if world > 1 else None
     scratch = torch.empty(B, dtype=torch.int64, device=dev)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     total_ms = 0.0
@@ -115,6 +116,11 @@ def main():
             out, gathered = d.lookup_batch(q), None
         e1.record()
         torch.cuda.synchronize()
+        if out.dtype != torch.int64:                      # 32-bit ids: widen for the checks (UINT32_MAX -> -1)
+            widen = lambda t: torch.where(t == -1, torch.full((), -1, dtype=torch.int64, device=t.device), t.to(torch.int64) & 0xFFFFFFFF)
+            out = widen(out)
+            if gathered is not None:
+                gathered = widen(gathered)
         # positives return the sampled ids -- except where the (regular) index holds a k-mer AND its
         # reverse complement as two entries (a 32-base reverse palindrome in the text: ~0.6 expected
         # in 2.5e9 random bases); those few must then agree with the reference CPU dictionary
@@ -168,10 +174,11 @@ def main():
             "config": "cfg5: k=%d m=%d synthetic human-scale index, query batch sharded across %d GPU(s), NCCL gather of ids to rank 0"
                       % (k, a.m, world),
             "index": os.path.basename(idx), "num_kmers": nk, "device_bytes_per_gpu": d.info["device_bytes"],
-            "n_gpus": world, "queries_total": nq, "queries_per_rank": n_batches * B, "batch_per_rank": B, "gather_mode": (sl.mode if sl is not None else None),
+            "n_gpus": world, "queries_total": nq, "queries_per_rank": n_batches * B, "batch_per_rank": B, "gather_mode": (sl.mode if sl is not None else None), "ids_bits": 32 if a.ids32 else 64,
             "mix": "50 % positive (half of them reverse-complemented), 50 % uniform random (negative)",
             "lookup_plus_gather": {"ms": total_ms, "lookups_per_s": nq / total_ms * 1e3,
-                                   "ids_bytes_to_rank0": (world - 1) * n_batches * B * 8},
+                                   "ids_bytes_to_rank0": (world - 1) * n_batches * B * (4 if a.ids32 else 8),
+                                   "rank0_ingress_GBps": (world - 1) * n_batches * B * (4 if a.ids32 else 8) / total_ms / 1e6},
             "per_batch_ms_rank0": per_batch_ms,
             "lookup_only": {"ms": lookup_only_ms, "lookups_per_s": nq / lookup_only_ms * 1e3},
             "random_kmers_found": found_neg, "reverse_palindrome_twins_rank0": rc_twins, "checked_vs_reference": oracle_checked,

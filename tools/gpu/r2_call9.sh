@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+nvidia-smi -L | head -3
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_c9_pytest.log 2>&1; tail -5 gpurun_out/r2_c9_pytest.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; tail -3 gpurun_out/r2_bench_n2.err; cat gpurun_out/r2_bench_n2.json
+ls -la gpurun_out/
