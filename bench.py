@@ -470,11 +470,14 @@ def main():
     s32 = time_e2e(lambda: d.lookup_batch_u32(h_in_np, out=h32_np), max(2, args.steps // 2), barrier, dev, world)
     assert torch.equal(widen_ids(h32), ids.cpu()), "e2e u32 ids differ from the sampled ids"
     e2e["u32_ids"] = {"value": world * n * max(2, args.steps // 2) / s32, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 4}
-    smem_ = time_e2e(lambda: d.is_member_batch(h_in_np), max(2, args.steps // 2), barrier, dev, world)
+    hmem = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    hmem_np = hmem.numpy()
+    smem_ = time_e2e(lambda: d.is_member_batch(h_in_np, out=hmem_np), max(2, args.steps // 2), barrier, dev, world)
+    assert bool(hmem.all()), "e2e membership: every query is a positive"
     e2e["is_member"] = {"value": world * n * max(2, args.steps // 2) / smem_, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n}
     e2e["note"] = ("host buffers: PCIe-bound; measured duplex ceiling of one B200 link here 46.6 GB/s per direction "
                    "(profiles/r1_pcie_duplex_e2e.json) = 5.83 G lookups/s at 8 B in + 8 B out")
-    del h32, h_out
+    del h32, h_out, hmem
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- N > 1: ONE process, ONE C-ABI handle over all N GPUs (sshash_gpu_multi_*), rank 0 only ------------

@@ -191,9 +191,14 @@ class Dictionary:
         return {n: int(r[n]) for n in RESULT_DTYPE.names}
 
     # ---- membership, include/dictionary.hpp:75-76 ---------------------------------------------
-    def is_member_batch(self, kmers, check_reverse_complement: bool = True, stream: Optional[int] = None):
+    def is_member_batch(self, kmers, check_reverse_complement: bool = True, stream: Optional[int] = None, out=None):
+        """member[i] = 1 iff found.  `out`: optional uint8 buffer (e.g. pinned) to receive the bytes as they are."""
         kmers = self._prep_in(kmers)
         n = self._count(kmers)
+        if out is not None:
+            check(self._lib.sshash_gpu_is_member_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(out),
+                                                       _stream_for(kmers, stream)))
+            return out
         out = self._alloc_like(kmers, n, np.uint8)
         check(self._lib.sshash_gpu_is_member_batch(self._h, _ptr(kmers), n, int(check_reverse_complement), _ptr(out),
                                                    _stream_for(kmers, stream)))
