@@ -333,6 +333,7 @@ def main():
     ap.add_argument("--queries", type=int, default=QUERIES_PER_GPU, help="queries per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scale", action="store_true", help="skip the HBM-resident 5e8-k-mer and the streaming secondary workloads")
+    ap.add_argument("--gather-chunk", type=int, default=1 << 22, help="N > 1: queries per lookup launch / per pushed piece of the gather")
     ap.add_argument("--no-ncu", action="store_true", help="do not measure roofline.traffic with an ncu pass after the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -426,11 +427,11 @@ def main():
 
         for ids32, modes in ((True, ("copy", "peer")), (False, ("copy", "peer", "p2p"))):
             for mode in modes:
-                sl = ShardedLookup.for_dictionary(d, chunk_queries=1 << 24, mode=mode, ids32=ids32)
+                sl = ShardedLookup.for_dictionary(d, chunk_queries=args.gather_chunk, mode=mode, ids32=ids32)
                 state = {}
 
                 def step_gather():
-                    state["r"] = sl.lookup(kmers, dst=0)
+                    state["r"] = sl.lookup(kmers, dst=0, sizes=[n] * world)
 
                 for _ in range(3):
                     step_gather()
@@ -475,8 +476,27 @@ def main():
     smem_ = time_e2e(lambda: d.is_member_batch(h_in_np, out=hmem_np), max(2, args.steps // 2), barrier, dev, world)
     assert bool(hmem.all()), "e2e membership: every query is a positive"
     e2e["is_member"] = {"value": world * n * max(2, args.steps // 2) / smem_, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n}
-    e2e["note"] = ("host buffers: PCIe-bound; measured duplex ceiling of one B200 link here 46.6 GB/s per direction "
-                   "(profiles/r1_pcie_duplex_e2e.json) = 5.83 G lookups/s at 8 B in + 8 B out")
+    # ceiling of the host-buffer leg, measured here: the same 8 B in + 8 B out per lookup moved concurrently by
+    # all ranks with no kernels at all (pinned memory, two streams, 32 MB pieces)
+    h_out = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    piece = (32 << 20) // 8
+
+    def duplex():
+        for lo in range(0, n, piece):
+            hi = min(n, lo + piece)
+            with torch.cuda.stream(s_in):
+                kmers[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out[lo:hi].copy_(out[lo:hi], non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
+    dsecs = time_e2e(duplex, 3, barrier, dev, world)
+    e2e["pcie_duplex_ceiling"] = {"value": world * n * 3 / dsecs, "unit": "lookups/s",
+                                  "GBps_per_direction_all_gpus": world * n * 8 * 3 / dsecs / 1e9,
+                                  "what": "16 B per lookup over PCIe, all %d rank(s) at once, no kernels" % world}
+    e2e["frac_of_pcie_ceiling"] = e2e_value / e2e["pcie_duplex_ceiling"]["value"]
     del h32, h_out, hmem
     clocks = sampler.stop() if rank == 0 else None
 

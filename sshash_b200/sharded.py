@@ -138,8 +138,9 @@ class ShardedLookup:
         hdl.barrier()
         return local_ids, (buf[:sum(sizes)] if self.rank == dst else None)
 
-    def lookup(self, local_kmers, dst: Optional[int] = 0):
-        """Look up this rank's shard.  Returns (local_ids, gathered) where `gathered` is, on rank
+    def lookup(self, local_kmers, dst: Optional[int] = 0, sizes: Optional[List[int]] = None):
+        """Look up this rank's shard.  `sizes`: the number of queries of EVERY rank when the caller knows them
+        (e.g. equal shards) -- saves the all_gather + host synchronisation that finds them out.  Returns (local_ids, gathered) where `gathered` is, on rank
         `dst`, the ids of ALL ranks concatenated in rank order (= global query order for shards made
         with shard_range); None elsewhere, or everywhere when dst is None.  In "peer" mode local_ids
         is this rank's slice of rank dst's vector (peer-mapped memory) and both results are valid
@@ -155,10 +156,13 @@ class ShardedLookup:
                 local_ids[lo:hi] = self.lookup_fn(local_kmers[lo * self.words:hi * self.words])
             return local_ids, (local_ids if (dst is not None and self.world == 1) else None)
         # sizes of all shards (ragged shards allowed)
-        sizes_t = [torch.zeros(1, dtype=torch.int64, device=local_kmers.device) for _ in range(self.world)]
-        dist.all_gather(sizes_t, torch.tensor([n_local], dtype=torch.int64, device=local_kmers.device),
-                        group=self.group)
-        sizes = [int(s.item()) for s in sizes_t]
+        if sizes is None:
+            sizes_t = [torch.zeros(1, dtype=torch.int64, device=local_kmers.device) for _ in range(self.world)]
+            dist.all_gather(sizes_t, torch.tensor([n_local], dtype=torch.int64, device=local_kmers.device),
+                            group=self.group)
+            sizes = [int(s.item()) for s in sizes_t]
+        elif len(sizes) != self.world or sizes[self.rank] != n_local:
+            raise ValueError("sizes must list every rank's shard size")
         starts = [sum(sizes[:r]) for r in range(self.world)]
         if self.mode == "peer":
             return self._lookup_peer(local_kmers, dst, sizes, starts)

@@ -53,6 +53,24 @@ def test_open_errors_without_cpu_fallback(tmp_path):
             sshash_b200.Dictionary(golden("se_k31_m13").index)
 
 
+def test_multi_gpu_handle_errors_without_a_gpu():
+    import ctypes as C
+    import torch
+    import sshash_b200
+    from sshash_b200 import _lib
+    lib = _lib.lib()
+    assert lib.sshash_gpu_multi_num_devices(None) == 0 and lib.sshash_gpu_multi_dict(None, 0) is None
+    assert lib.sshash_gpu_multi_lookup_batch(None, None, 1, 1, None) == 1          # EINVAL: null handle
+    assert b"null multi-GPU handle" in lib.sshash_gpu_last_error()
+    assert lib.sshash_gpu_multi_close(None) == 0
+    if not torch.cuda.is_available():
+        with pytest.raises(sshash_b200.SshashGpuError, match="no CUDA device"):
+            sshash_b200.MultiDictionary(golden("se_k31_m13").index)
+        h = C.c_void_p()
+        devs = (C.c_int * 2)(0, 0)
+        assert lib.sshash_gpu_multi_open(golden("se_k31_m13").index.encode(), devs, 2, 0, C.byref(h)) == 5 and not h
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sshash_b200")):
         for f in files:
