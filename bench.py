@@ -425,8 +425,9 @@ def main():
                 got = torch.stack([sl.sum(), (sl * w_local).sum()])
                 assert torch.equal(got, sums[r]), "gathered ids of rank %d are wrong (%s)" % (r, what)
 
-        for ids32, modes in ((True, ("copy", "peer")), (False, ("copy", "peer", "p2p"))):
+        for ids32, modes in ((True, ("copy", "staged", "peer")), (False, ("copy", "staged", "peer", "p2p"))):
             for mode in modes:
+                key = ("u32_" if ids32 else "u64_") + mode
                 sl = ShardedLookup.for_dictionary(d, chunk_queries=args.gather_chunk, mode=mode, ids32=ids32)
                 state = {}
 
@@ -442,7 +443,6 @@ def main():
                 local_ids, gathered = state["r"]
                 assert torch.equal(widen_ids(local_ids), ids), "local ids differ from the sampled ids"
                 verify(gathered, "%s ids, mode %s" % ("u32" if ids32 else "u64", mode))
-                key = ("u32_" if ids32 else "u64_") + mode
                 bytes_in = (world - 1) * n * (4 if ids32 else 8)
                 gather[key] = {"ms_per_step": g_ms / args.steps, "lookups_per_s": world * n * args.steps / (g_ms * 1e-3),
                                "rank0_ingress_GBps": bytes_in * args.steps / (g_ms * 1e-3) / 1e9, "launches": int(g_launches)}

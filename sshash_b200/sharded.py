@@ -17,6 +17,10 @@ resulting ids -- there is no exchange step inside the algorithm.  Two gather mod
           next chunk is looked up.  For many senders: the 8-byte stores of "peer" mode that come out
           of the reverse-complement queue are scattered, and 7 ranks of them fill rank 0's NVLink
           ingress at ~300 GB/s, whereas the copy engines move full-size packets.
+  "staged" the same data movement as "copy", but driven inside the library: rank r hands the C ABI its
+          slice of rank dst's vector as the output pointer with peer-inplace OFF, and the library's
+          own chunk pipeline (api.cu run_batched: kernel of chunk c into a staging buffer, copy-engine
+          push of chunk c-1, three streams) delivers it -- no per-chunk Python / event overhead.
   "p2p"   chunked isend/irecv of locally written ids, overlapped with the next chunk's lookup
           kernel (NCCL on GPUs; gloo in the CPU tests, where the lookup function is injected).  An
           NCCL send kernel needs SMs the persistent lookup CTAs hold, so this mode costs the full
@@ -53,9 +57,9 @@ class ShardedLookup:
         self.chunk = int(chunk_queries)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        if mode not in ("p2p", "peer", "copy"):
-            raise ValueError("mode must be 'p2p', 'peer' or 'copy'")
-        if mode in ("peer", "copy") and lookup_into is None:
+        if mode not in ("p2p", "peer", "copy", "staged"):
+            raise ValueError("mode must be 'p2p', 'peer', 'copy' or 'staged'")
+        if mode in ("peer", "copy", "staged") and lookup_into is None:
             raise ValueError("mode '%s' needs lookup_into" % mode)
         self.mode = mode
         if ids_dtype is None:
@@ -103,6 +107,9 @@ class ShardedLookup:
         buf, hdl, remote = self._gathered_buffer(sum(sizes), dst, local_kmers.device)
         mine = remote[starts[self.rank]:starts[self.rank] + n_local]
         hdl.barrier()                                    # rank dst has consumed the previous result (stream order)
+        if self.mode == "staged":
+            import torch
+            torch.cuda.current_stream(local_kmers.device).synchronize()   # the library pipelines on its own streams
         if n_local:
             self.lookup_into(local_kmers, mine)          # ids go over NVLink into rank dst's vector
         hdl.barrier()                                    # on the current stream: every rank's stores are done
@@ -164,7 +171,7 @@ class ShardedLookup:
         elif len(sizes) != self.world or sizes[self.rank] != n_local:
             raise ValueError("sizes must list every rank's shard size")
         starts = [sum(sizes[:r]) for r in range(self.world)]
-        if self.mode == "peer":
+        if self.mode in ("peer", "staged"):      # same call; the dictionary's peer-inplace switch decides who moves the ids
             return self._lookup_peer(local_kmers, dst, sizes, starts)
         if self.mode == "copy":
             return self._lookup_copy(local_kmers, dst, sizes, starts)

@@ -32,4 +32,14 @@ for it in range(n_iter):
     stats[r] = stats.get(r, 0) + 1
     if dt > 5: print("slow", it, dt, r)
 os.remove(tmp)
+# after the damaged files the same process must still be able to open and query the good one (no sticky CUDA error)
+try:
+    import numpy as np
+    d = sshash_b200.Dictionary(src, max_k=0 if "k63" not in src and "k47" not in src else 63)
+    q = d.access_batch(np.arange(0, min(1000, d.num_kmers()), dtype=np.uint64))
+    assert (d.lookup_batch(q.reshape(-1)) != np.uint64(2**64 - 1)).all()
+    d.close()
+except sshash_b200.SshashGpuError as e:
+    if "no CUDA device" not in str(e):
+        raise
 print(stats)

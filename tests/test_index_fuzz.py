@@ -38,3 +38,20 @@ def test_corrupted_header_fields_never_crash_the_loader(name):
     stats = run(golden(name).index, 12, 150, "flip", span=48)
     assert "opened" not in stats and set(stats) <= {"EFORMAT", "EVERSION", "EINVAL", "ECUDA"}, stats
     assert stats.get("EFORMAT", 0) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sal100_k31_m7_reg", "se_k31_m13"])
+def test_corrupted_files_on_a_gpu_open_cleanly_or_are_rejected(name):
+    """With a GPU the open goes all the way: parse, upload, the open-time validation kernel (every control
+    codeword and bucket offset is range-checked), the fingerprint build.  Bit flips anywhere in the file must
+    give `opened` or a status code -- never a crash or a sticky CUDA error -- and a good file must still open
+    and answer correctly in the same process afterwards (the helper does that last step itself)."""
+    import numpy as np
+    import sshash_b200
+    g = golden(name)
+    stats = run(g.index, 13, 80, "flip", span=1 << 30)
+    assert set(stats) <= {"opened", "EFORMAT", "EVERSION", "EINVAL"}, stats
+    d = sshash_b200.Dictionary(g.index, max_k=g.max_k)
+    assert (d.lookup_batch(g.z["queries"]) == g.z["ids"]).all()
+    d.close()

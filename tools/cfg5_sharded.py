@@ -44,7 +44,7 @@ def main():
     ap.add_argument("--batch", type=int, default=125_000_000)
     ap.add_argument("--oracle-sample", type=int, default=1_000_000)
     ap.add_argument("--chunk", type=int, default=1 << 23, help="p2p mode: queries per lookup launch / per send of the gather")
-    ap.add_argument("--mode", default="auto", choices=["auto", "peer", "copy", "p2p"],
+    ap.add_argument("--mode", default="auto", choices=["auto", "peer", "copy", "staged", "p2p"],
                     help="gather: ids stored straight into rank 0's vector over NVLink (peer) or NCCL send/recv (p2p)")
     ap.add_argument("--ids32", action="store_true", help="gather 32-bit ids (sshash_gpu_lookup_batch_u32): half the bytes into rank 0")
     a = ap.parse_args()
