@@ -71,14 +71,15 @@ class ShardedLookup:
 
     @classmethod
     def for_dictionary(cls, dictionary, group=None, chunk_queries: int = 1 << 25, mode: str = "auto", ids32: bool = False):
-        """mode "auto": on NCCL (GPUs of one box) peer stores for 2 ranks, copy engines beyond (rank dst's
-        NVLink ingress is the limit there and scattered 8-byte stores use it badly: measured at N=8 on
-        a 2.5e9-k-mer index 18.8 ms per 8 x 1.25e8 lookups with "copy", 25.9 with "peer", 26.8 with
-        "p2p"; at N=2 on cfg2 4.9 / 5.6 / 7.1 ms for peer / copy / p2p); p2p on other backends."""
+        """mode "auto": on NCCL (GPUs of one box) peer stores for 2 ranks, the library-staged copy-engine
+        pipeline beyond (rank dst's NVLink ingress is the limit there and the scattered stores that leave the
+        reverse-complement queue use it badly); p2p on other backends.  Measured on cfg2, 1e8 queries per
+        rank, 32-bit ids: N=2 4.90 / 5.09 / 5.83 ms for peer / staged / copy (the Python-driven "copy" pays
+        ~60 us of host time per piece); N=8 9.5 / - / 5.9 ms."""
         import torch.distributed as dist
         if mode == "auto":
             if dist.get_backend(group) == "nccl" and dist.get_world_size(group) > 1:
-                mode = "peer" if dist.get_world_size(group) <= 2 else "copy"
+                mode = "peer" if dist.get_world_size(group) <= 2 else "staged"
             else:
                 mode = "p2p"
         import torch
