@@ -191,6 +191,16 @@ SSHASH_GPU_API int sshash_gpu_string_neighbours_batch(const sshash_gpu_dict* dic
                                                       sshash_lookup_result* full, void* stream);
 
 /*
+ * Does the index keep SSHash's input contract (README: "without duplicate k-mers") -- every
+ * k-mer once and, on a regular index, never together with its reverse complement?  Checked on the
+ * device (two lookups per text offset), once per handle, lazily at the first streaming call or here.
+ * *breaks_contract = 1: streaming over this index replays the reference's state machine literally
+ * (include/streaming_query.hpp:56-197), because the reference's own answers then depend on the state
+ * of the stream; 0: the alignment / classification shortcuts are exact and are used.
+ */
+SSHASH_GPU_API int sshash_gpu_check_input_contract(const sshash_gpu_dict* dict, int* breaks_contract);
+
+/*
  * Streaming membership over a batch of reads: replaces streaming_query<Dict,canonical>::lookup
  * driven per read as in streaming_query_from_fastq_file (include/streaming_query.hpp:56-115,
  * src/query.cpp:78-108): reset per read, reads shorter than k skipped, a window containing a

@@ -65,6 +65,7 @@ SYMBOLS = {
                                                    C.c_void_p]),
     "sshash_gpu_string_neighbours_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                                      C.c_void_p]),
+    "sshash_gpu_check_input_contract": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "sshash_gpu_streaming_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                              C.POINTER(StreamingReport), C.c_void_p]),
     "sshash_gpu_streaming_query_from_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(StreamingReport)]),

@@ -949,6 +949,18 @@ static int needs_replay(const sshash_gpu_dict* dict, bool* replay) {
     return SSHASH_GPU_OK;
 }
 
+extern "C" {
+SSHASH_ENTRY(sshash_gpu_check_input_contract, (const sshash_gpu_dict* dict, int* breaks_contract), (dict, breaks_contract)) {
+    int st = check_dict(dict);
+    if (st) return st;
+    if (!breaks_contract) return fail(SSHASH_GPU_EINVAL, "null argument");
+    bool replay = false;
+    st = needs_replay(dict, &replay);
+    *breaks_contract = replay ? 1 : 0;
+    return st;
+}
+}
+
 // One device-resident batch of reads: offsets scan, window lookups, state-machine replay.
 static int streaming_device(const sshash_gpu_dict* dict, Workspace& w, const char* d_bases, const uint64_t* d_read_begins,
                             const uint64_t* d_read_ends, uint64_t num_reads, uint64_t max_windows, uint64_t* d_ids_out, cudaStream_t s) {

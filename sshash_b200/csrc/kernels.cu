@@ -960,7 +960,8 @@ stream_classify_kernel(const uint64_t* __restrict__ win_offsets, uint64_t num_re
 template <int W>
 __global__ void __launch_bounds__(kBlock)
 distinct_check_kernel(const __grid_constant__ DeviceIndex ix, uint32_t* __restrict__ flag) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n_bases = ix.strings_bits / 2;
+    // the text ends at the last end-point; `strings` may hold a few more (sentinel / padding) bits
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n_bases = ix.ends[ix.n_ends - 1];
     const uint32_t k = ix.k;
     bool bad = false;
     for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o + k <= n_bases; o += stride) {

@@ -252,6 +252,13 @@ class Dictionary:
                                                            _ptr(out) if full else None, None))
         return out
 
+    def breaks_input_contract(self) -> bool:
+        """True when the index holds duplicated k-mers or (regular index) reverse-complement twins: streaming
+        then replays the reference's state machine instead of using the shortcuts (checked on the device once)."""
+        flag = C.c_int(0)
+        check(self._lib.sshash_gpu_check_input_contract(self._h, C.byref(flag)))
+        return bool(flag.value)
+
     # ---- streaming, include/streaming_query.hpp + src/query.cpp -------------------------------
     def streaming_batch(self, bases, read_offsets, want_ids: bool = True, stream: Optional[int] = None):
         """Streaming membership over a batch of reads (concatenated characters + offsets).

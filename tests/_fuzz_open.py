@@ -18,7 +18,7 @@ for it in range(n_iter):
         for _ in range(rnd.randrange(1, 4)):
             # favour the structural fields: headers of the nested containers are spread over the file,
             # so flip anywhere, with a bias to the first 64 KB
-            pos = rnd.randrange(0, int(os.environ.get("FUZZ_SPAN", "65536"))) if rnd.random() < 0.5 else rnd.randrange(0, len(b))
+            pos = rnd.randrange(0, min(len(b), int(os.environ.get("FUZZ_SPAN", "65536")))) if rnd.random() < 0.5 else rnd.randrange(0, len(b))
             b[pos] = rnd.randrange(256) if rnd.random() < 0.5 else (b[pos] ^ (1 << rnd.randrange(8)))
     open(tmp, "wb").write(b)
     t0 = time.time()

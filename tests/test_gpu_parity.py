@@ -624,6 +624,13 @@ def test_concurrent_batches_on_one_handle(dicts):
     assert not errors, errors
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_input_contract_check_flags_exactly_the_non_distinct_indexes(dicts, name):
+    """distinct_check_kernel: the twin / duplicate fixtures break SSHash's input contract, no other fixture does
+    (a false positive would silently cost the streaming shortcuts: 2x slower, still correct)."""
+    assert dicts(name).breaks_input_contract() == (golden(name).meta.get("distinct_kmers") is False)
+
+
 @pytest.mark.parametrize("name", ["se_k31_m13", "sal100_k31_m7_canon", "sal100_k31_m7_reg", "twins_k31_m13_reg"])
 def test_streaming_replay_path_equals_the_shortcuts(name):
     """SSHASH_GPU_ASSUME_DISTINCT=0 forces the literal replay of the reference's state machine (the path
