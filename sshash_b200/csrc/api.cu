@@ -333,15 +333,18 @@ int upload_index(sshash_gpu_dict* d, const IndexFile& f, int max_k) {
     if (ends.size() >> 32) return fail(SSHASH_GPU_EFORMAT, "unsupported index: >= 2^32 strings");
     const uint64_t U = ends.back();
     if (2 * U > f.strings.num_bits) return fail(SSHASH_GPU_EFORMAT, "malformed index file (end-points beyond the strings)");
-    // Directory granularity: about two blocks per string (a block then holds 0.5 end-points on average,
-    // so locate_string's scan rarely takes a step), between 2^6 and 2^16 bases.  SSHASH_GPU_LOCATE=legacy
-    // keeps round 1's fixed 2^8 blocks and 64-bit end-points (A/B switch).
+    // Directory granularity: about two blocks per string (a block then holds 0.5 end-points on average, so
+    // locate_string's scan takes half a step), but never fewer than 2^20 blocks while blocks stay >= 2^6
+    // bases: a small index gets a fine directory (4 MB at most, no scan steps at all), a huge one a compact one
+    // (2.5e9 k-mers: 60 MB -> 30 MB of locate tables).  SSHASH_GPU_LOCATE=legacy keeps round 1's fixed 2^8
+    // blocks and 64-bit end-points (A/B switch).
     const char* loc_env = std::getenv("SSHASH_GPU_LOCATE");
     const bool legacy_locate = loc_env && std::strcmp(loc_env, "legacy") == 0;
     ix.dir_shift = 8;
     if (!legacy_locate) {
+        const uint64_t max_blocks = std::max<uint64_t>(2 * ends.size(), 1ull << 20);
         ix.dir_shift = 6;
-        while (ix.dir_shift < 16 && (U >> ix.dir_shift) > 2 * ends.size()) ++ix.dir_shift;
+        while (ix.dir_shift < 16 && (U >> ix.dir_shift) > max_blocks) ++ix.dir_shift;
     }
     std::vector<uint32_t> dir(((f.strings.num_bits / 2) >> ix.dir_shift) + 2);   // every offset the validated buckets can hold
     {   // dir[h] = index of the last end-point < (h << shift), 0 if none
@@ -556,14 +559,10 @@ void configure_l2(sshash_gpu_dict* d) {
     // Pilots that cannot stay resident next to the locate tables are loaded like the other cold arrays
     // (evict_first, 64-byte fills) and the window shrinks to the slab's prefix (SSHASH_GPU_PILOTS_COLD=0/1 forces).
     // Measured on the 2.5e9-k-mer index (profiles/r2_exp_locality_v1.jsonl): a partially resident pilots pool
-    // (evict_last, window over the whole slab with hitRatio = persisting / window) beats the cold policy
-    // (13.5 vs 12.8 G lookups/s forward, 13.3 vs 10.7 negative), so cold pilots are opt-in only.
-    bool cold = false;
-    d->ix.pilots_cold = 0;
-    if (const char* pc = std::getenv("SSHASH_GPU_PILOTS_COLD")) {       // 1: cold policy, 2: evict_last with 64-byte fills
-        cold = pc[0] == '1';
-        d->ix.pilots_cold = pc[0] == '1' ? 1 : pc[0] == '2' ? 2 : 0;
-    }
+    // (evict_last, window over the whole slab with hitRatio = persisting / window) beats a cold-policy pool
+    // (13.5 vs 12.8 G lookups/s forward, 13.3 vs 10.7 negative) and evict_last with 64-byte fills makes no
+    // difference, so the pilots keep the hot policy at every index size (the A/B switches are gone).
+    const bool cold = false;
     // SSHASH_GPU_L2_WINDOW=prefix: the window covers only the locate tables (the pilots keep their evict_last hint)
     const char* we = std::getenv("SSHASH_GPU_L2_WINDOW");
     const bool prefix_only = cold || (we && std::strcmp(we, "prefix") == 0);

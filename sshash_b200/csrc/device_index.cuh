@@ -85,8 +85,7 @@ struct DeviceIndex {
     const uint32_t* ends_dir;
     const uint32_t* ends32;            // the same end-points as u32 when the last one is < 2^32 - 1 (else nullptr):
                                        // locate_string reads these, half the bytes to keep L2-resident
-    uint32_t pilots_cold;              // 1 = the pilots pool does not fit the persisting part of L2: its loads
-    uint32_t pad3_;                    // take the cold policy (evict_first, 64-byte fills) like codewords / strings
+    uint32_t pad3_[2];
     // weights (include/weights.hpp:148-153,182-187); n_weight_intervals == 0 <=> not weighted
     const uint64_t* weight_starts;     // n_weight_intervals + 1 entries (+ sentinels)
     const uint32_t* weight_dir;        // weight_dir[h] = index of the last start <= (h << weight_dir_shift)
@@ -477,11 +476,9 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
     const uint64_t h1 = h.first;
     const uint64_t H = __umul64hi(__umul64hi(h1, h1), (h1 >> 1) | (1ull << 63)) / 8 * 7 + h1 / 8;
     const uint32_t bucket = mulhi_64x32(H, num_buckets);
-    const uint64_t* pw = ix.pilots + pilots_word;
-    const uint64_t pilot = BINNED ? compact_get<kNormal>(pw, pilot_width, low_mask(pilot_width), bucket)
-                           : ix.pilots_cold == 1 ? compact_get<kCold>(pw, pilot_width, low_mask(pilot_width), bucket)
-                           : ix.pilots_cold == 2 ? compact_get<kHot64>(pw, pilot_width, low_mask(pilot_width), bucket)
-                                                 : compact_get<kHot>(pw, pilot_width, low_mask(pilot_width), bucket);
+    // pilots: evict_last in the direct kernels (a partially resident pool beats the cold policy even when it
+    // outgrows L2: measured), plain loads in the partition-major path (L2 hits by schedule)
+    const uint64_t pilot = compact_get<BINNED ? kNormal : kHot>(ix.pilots + pilots_word, pilot_width, low_mask(pilot_width), bucket);
     uint32_t pos = mulhi_64x32((h.second ^ (pilot * SSHASH_MIX_C)) * SSHASH_MIX_C, table_size);
     if (pos >= num_keys) pos = ld32<true>(ix.free_slots + free_off + (pos - num_keys));
     return offset + pos;
@@ -492,18 +489,22 @@ __device__ __forceinline__ uint64_t phf_position(const DeviceIndex& ix, const De
 // endpoints_sequence::locate (endpoints_sequence.hpp:182-198).  Returns the index of the largest
 // end-point <= x; begin/end are that end-point and the next.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_t x, uint64_t& begin, uint64_t& end) {
-    // ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none): ends[i] <= x holds
+// texts of 2^32 - 1 bases or more keep 64-bit end-points: out of line, so that the common path stays small
+static __device__ __noinline__ uint64_t locate_string_u64(const DeviceIndex& ix, uint64_t x, uint64_t& begin, uint64_t& end) {
     uint64_t i = ld32<true>(ix.ends_dir + (x >> ix.dir_shift));
-    if (ix.ends32) {
-        uint32_t cur = ld32<true>(ix.ends32 + i), next = ld32<true>(ix.ends32 + i + 1);
-        while (next <= x) { cur = next; ++i; next = ld32<true>(ix.ends32 + i + 1); }
-        begin = cur; end = next;
-        return i;
-    }
     uint64_t cur = ld64<true>(ix.ends + i), next = ld64<true>(ix.ends + i + 1);
-    // advance to the last end-point <= x; at most (1 << dir_shift) / k + 1 steps
     while (next <= x) { cur = next; ++i; next = ld64<true>(ix.ends + i + 1); }
+    begin = cur; end = next;
+    return i;
+}
+__device__ __forceinline__ uint64_t locate_string(const DeviceIndex& ix, uint64_t x, uint64_t& begin, uint64_t& end) {
+    if (!ix.ends32) return locate_string_u64(ix, x, begin, end);
+    // ends_dir[h] = index of the last end-point < (h << dir_shift) (0 if none): ends[i] <= x holds;
+    // advance to the last end-point <= x (about half a step on average: two directory blocks per string)
+    const uint32_t x32 = (uint32_t)x;                       // the text has < 2^32 - 1 bases here
+    uint32_t i = ld32<true>(ix.ends_dir + (x32 >> ix.dir_shift));
+    uint32_t cur = ld32<true>(ix.ends32 + i), next = ld32<true>(ix.ends32 + i + 1);
+    while (next <= x32) { cur = next; ++i; next = ld32<true>(ix.ends32 + i + 1); }
     begin = cur; end = next;
     return i;
 }
