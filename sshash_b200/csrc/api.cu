@@ -556,16 +556,13 @@ void configure_l2(sshash_gpu_dict* d) {
     const char* e = std::getenv("SSHASH_GPU_L2_PERSIST");
     const bool want = !(e && e[0] == '0');
     c.window_bytes = 0;
-    // Pilots that cannot stay resident next to the locate tables are loaded like the other cold arrays
-    // (evict_first, 64-byte fills) and the window shrinks to the slab's prefix (SSHASH_GPU_PILOTS_COLD=0/1 forces).
-    // Measured on the 2.5e9-k-mer index (profiles/r2_exp_locality_v1.jsonl): a partially resident pilots pool
+    // Slabs beyond the persisting capacity (human-scale pilots).  Measured on the 2.5e9-k-mer index (profiles/r2_exp_locality_v1.jsonl): a partially resident pilots pool
     // (evict_last, window over the whole slab with hitRatio = persisting / window) beats a cold-policy pool
     // (13.5 vs 12.8 G lookups/s forward, 13.3 vs 10.7 negative) and evict_last with 64-byte fills makes no
     // difference, so the pilots keep the hot policy at every index size (the A/B switches are gone).
-    const bool cold = false;
     // SSHASH_GPU_L2_WINDOW=prefix: the window covers only the locate tables (the pilots keep their evict_last hint)
     const char* we = std::getenv("SSHASH_GPU_L2_WINDOW");
-    const bool prefix_only = cold || (we && std::strcmp(we, "prefix") == 0);
+    const bool prefix_only = we && std::strcmp(we, "prefix") == 0;
     const uint64_t span = prefix_only ? std::max<uint64_t>(c.hot_prefix_bytes, 256) : c.hot_bytes;
     if (want && c.max_window_bytes && c.max_persist_bytes && span) {
         size_t cur = 0;

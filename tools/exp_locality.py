@@ -22,9 +22,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 VARIANTS = {
     "r1_layout": {"SSHASH_GPU_LOCATE": "legacy", "SSHASH_GPU_BINNED": "0"},
     "direct": {"SSHASH_GPU_BINNED": "0"},
-    "direct+pilots_cold": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "1"},
+    # (the pilot-policy variants "direct+pilots_cold" / "+pilots_hot64" of profiles/r2_exp_locality_v1.jsonl needed
+    #  switches that were removed from the library after they lost)
     "direct+prefix_window": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_L2_WINDOW": "prefix"},
-    "direct+pilots_hot64": {"SSHASH_GPU_BINNED": "0", "SSHASH_GPU_PILOTS_COLD": "2"},
     "binned": {"SSHASH_GPU_BINNED": "1"},
     "binned_noprefetch": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_PREFETCH": "0"},
     "binned_lookahead2": {"SSHASH_GPU_BINNED": "1", "SSHASH_GPU_BIN_LOOKAHEAD": "2"},
