@@ -49,6 +49,10 @@ class ShardedLookup:
     def __init__(self, lookup_fn: Callable, words: int = 1, group=None, chunk_queries: int = 1 << 25,
                  lookup_into: Optional[Callable] = None, mode: str = "p2p", ids_dtype=None):
         import torch.distributed as dist
+        if mode not in ("p2p", "peer", "copy", "staged"):
+            raise ValueError("mode must be 'p2p', 'peer', 'copy' or 'staged'")
+        if mode in ("peer", "copy", "staged") and lookup_into is None:
+            raise ValueError("mode '%s' needs lookup_into" % mode)
         self.dist = dist
         self.lookup_fn = lookup_fn
         self.lookup_into = lookup_into       # lookup_into(kmers, out): ids written into `out` (any device pointer)
@@ -57,10 +61,6 @@ class ShardedLookup:
         self.chunk = int(chunk_queries)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        if mode not in ("p2p", "peer", "copy", "staged"):
-            raise ValueError("mode must be 'p2p', 'peer', 'copy' or 'staged'")
-        if mode in ("peer", "copy", "staged") and lookup_into is None:
-            raise ValueError("mode '%s' needs lookup_into" % mode)
         self.mode = mode
         if ids_dtype is None:
             import torch

@@ -25,6 +25,14 @@ def test_shard_range_properties():
                 pos = hi
 
 
+def test_modes_that_write_into_the_root_vector_need_lookup_into():
+    for mode in ("peer", "copy", "staged"):
+        with pytest.raises(ValueError, match="needs lookup_into"):
+            ShardedLookup(lambda k: k, mode=mode)
+    with pytest.raises(ValueError, match="mode must be"):
+        ShardedLookup(lambda k: k, mode="nccl")
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -56,6 +64,19 @@ def _worker(rank, world, port, n, chunk, words, q):
             ok = ok and gathered is None
         _, none = sl.lookup(local, dst=None)
         ok = ok and none is None
+        # caller-provided shard sizes skip the all_gather; 32-bit ids travel as int32
+        sl32 = ShardedLookup(lambda c: (c.view(-1, words)[:, 0] % 1000).to(torch.int32), words=words, chunk_queries=chunk,
+                             ids_dtype=torch.int32)
+        ids32, g32 = sl32.lookup(local, dst=0, sizes=shard_sizes(n, world))
+        exp32 = (kmers.view(-1, words)[:, 0] % 1000).to(torch.int32)
+        ok = ok and ids32.dtype == torch.int32 and torch.equal(ids32, exp32[lo:hi])
+        if rank == 0:
+            ok = ok and torch.equal(g32, exp32)
+        try:
+            sl32.lookup(local, dst=0, sizes=[n] * (world + 1))
+            ok = False
+        except ValueError:
+            pass
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
