@@ -1252,7 +1252,7 @@ int stream_file_device_parse(const sshash_gpu_dict* dict, const char* filename, 
         ho.cv.notify_all();
         if (records) {
             CU(cudaStreamWaitEvent(s, w.file_counted[slot], 0));
-            CU(ensure(w.d_line_start, w.ls_cap, (lines + 2) * 8));   // (grows only while the compute stream is idle or after a sync below)
+            CU(ensure(w.d_line_start, w.ls_cap, (lines + 2) * 8));   // growing = cudaFree + cudaMalloc: cudaFree waits for the device, so chunk c-1 cannot be using the old buffer
             CU(ensure(w.d_spans, w.spans_cap, 2 * records * 8));
             CU(launch_read_spans(d_raw, n, d_tiles, w.d_line_start, records, stride, w.d_spans, w.d_spans + records,
                                  dict->ctx.sm_count, s));
