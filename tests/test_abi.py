@@ -71,6 +71,31 @@ def test_multi_gpu_handle_errors_without_a_gpu():
         assert lib.sshash_gpu_multi_open(golden("se_k31_m13").index.encode(), devs, 2, 0, C.byref(h)) == 5 and not h
 
 
+def test_header_is_plain_c_and_examples_compile(tmp_path):
+    """include/sshash_gpu.h is a C header (gcc -std=c99 -pedantic); the C and C++ examples build against the
+    library and, on a box without a GPU, fail loudly with the library's message instead of computing on the CPU."""
+    import subprocess
+    import torch
+    lib_dir = os.path.join(ROOT, "sshash_b200")
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include "sshash_gpu.h"\nint main(void) { return sizeof(sshash_lookup_result) == 64 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(probe), "-o", str(tmp_path / "probe")])
+    assert subprocess.run([str(tmp_path / "probe")]).returncode == 0
+    builds = [("gcc", ["-std=c11"], "multi_gpu_example.c"), ("g++", ["-std=c++17"], "lookup_example.cpp"),
+              ("g++", ["-std=c++17"], "query_example.cpp")]
+    for cc, flags, src in builds:
+        cc = "/usr/bin/" + cc if os.path.exists("/usr/bin/" + cc) else cc
+        exe = str(tmp_path / src.split(".")[0])
+        subprocess.check_call([cc, *flags, "-O1", "-Wall", "-Wextra", os.path.join(ROOT, "examples", src), "-o", exe,
+                               os.path.join(lib_dir, "libsshash_gpu.so"), "-Wl,-rpath," + lib_dir])
+    if not torch.cuda.is_available():
+        out = subprocess.run([str(tmp_path / "multi_gpu_example"), golden("se_k31_m13").index, "1000"], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
+        out = subprocess.run([str(tmp_path / "lookup_example"), golden("se_k31_m13").index, "1000"], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sshash_b200")):
         for f in files:
